@@ -1,0 +1,86 @@
+// CRC32 (IEEE 802.3, reflected, as in gzip) of every inflated BGZF block, compared with the
+// block trailer — the check noodles-bgzf performs on each block it reads.
+// One warp per block: every lane runs a byte-wise table CRC over its own contiguous slice,
+// then the 32 partial CRCs are merged with CRC(A||B) = CRC(A) * x^(8|B|) mod P  xor  CRC(B),
+// a carry-less multiply modulo the CRC polynomial (no 32x32 GF(2) matrices needed).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "inflate.cuh"
+
+namespace ngsq {
+
+constexpr uint32_t kCrcPoly = 0xEDB88320u;
+
+__host__ __device__ inline uint32_t crc_multmodp(uint32_t a, uint32_t b) {
+  uint32_t m = 1u << 31, p = 0;
+  for (;;) {
+    if (a & m) {
+      p ^= b;
+      if ((a & (m - 1)) == 0) break;
+    }
+    m >>= 1;
+    b = (b & 1) ? (b >> 1) ^ kCrcPoly : b >> 1;
+  }
+  return p;
+}
+
+struct CrcTables {
+  uint32_t byte_table[256];
+  uint32_t x2n[32];  // x^(2^n) mod P
+};
+
+inline void crc_make_tables(CrcTables& t) {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
+    t.byte_table[i] = c;
+  }
+  uint32_t p = 1u << 30;  // x^1
+  t.x2n[0] = p;
+  for (int n = 1; n < 32; ++n) t.x2n[n] = p = crc_multmodp(p, p);
+}
+
+// x^(n * 2^k) mod P
+__device__ __forceinline__ uint32_t crc_x2nmodp(const uint32_t* x2n, uint32_t n, uint32_t k) {
+  uint32_t p = 1u << 31;  // x^0
+  while (n) {
+    if (n & 1) p = crc_multmodp(x2n[k & 31], p);
+    n >>= 1;
+    ++k;
+  }
+  return p;
+}
+
+__global__ void __launch_bounds__(256)
+crc32_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, const uint32_t* __restrict__ expect,
+             uint32_t n_blocks, const CrcTables* __restrict__ tables, uint32_t* __restrict__ n_bad) {
+  __shared__ uint32_t tab[256];
+  __shared__ uint32_t x2n[32];
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = tables->byte_table[i];
+  if (threadIdx.x < 32) x2n[threadIdx.x] = tables->x2n[threadIdx.x];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_blocks; b += warps) {
+    const BlockDesc d = blocks[b];
+    const uint8_t* p = out + d.out_off;
+    const uint32_t n = d.isize;
+    uint32_t per = ((n + 31) / 32 + 3) & ~3u;
+    uint32_t lo = lane * per, hi = lo + per;
+    if (lo > n) lo = n;
+    if (hi > n) hi = n;
+    uint32_t c = 0xFFFFFFFFu;
+    for (uint32_t i = lo; i < hi; ++i) c = tab[(c ^ p[i]) & 255] ^ (c >> 8);
+    c ^= 0xFFFFFFFFu;  // standard CRC of this slice (CRC of the empty string is 0)
+    // shift by the bytes that follow this slice, then xor-reduce
+    uint32_t after = n - hi;
+    if (hi > lo && after) c = crc_multmodp(crc_x2nmodp(x2n, after, 3), c);
+    if (hi == lo) c = 0;
+    for (int o = 16; o; o >>= 1) c ^= __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if (lane == 0 && c != expect[b]) atomicAdd(n_bad, 1u);
+  }
+}
+
+}  // namespace ngsq

@@ -1,0 +1,266 @@
+// K4-K8 — one fused pass over the inflated records: General, Template Length, GC Content,
+// Quality Score and the Coverage difference-array scatter.  Restates, per record, the
+// process() bodies of the reference facets:
+//   general.rs:31-124, template_length.rs:79-87, gc_content.rs:38-100,
+//   quality_scores.rs:37-49, coverage.rs:148-180 (+ the query filter of command.rs:369-377).
+//
+// One warp per record (grid-stride).  Flag-derived counters are uniform across the warp, so
+// every lane owns one counter in a register (lane k adds bit k of the record's counter mask):
+// no atomics at all for General / record tallies.  Histograms (tlen, gc, per-position quality,
+// CIGAR kinds) are privatised in shared memory per CTA and flushed once with 64-bit global
+// reductions.  Quality positions beyond the shared-memory table (long reads) go straight to
+// the L2-resident global table.  Coverage is two signed global reductions per record into the
+// contig's int32 difference array (coverage is span-based: SURVEY F6).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "recscan.cuh"
+
+namespace ngsq {
+
+// ---- layout of the packed u64 result buffer (also the NCCL reduce payload) ----
+constexpr uint32_t R_GENERAL = 0;       // 16
+constexpr uint32_t R_CIGAR = 16;        // 2 x 9
+constexpr uint32_t R_TLEN_HIST = 34;    // 1025
+constexpr uint32_t R_TLEN_PROCESSED = 1059;
+constexpr uint32_t R_TLEN_IGNORED = 1060;
+constexpr uint32_t R_GC_HIST = 1061;    // 101
+constexpr uint32_t R_GC_NUC = 1162;     // gc, at, other
+constexpr uint32_t R_GC_REC = 1165;     // processed, ignored_flags, ignored_too_short
+constexpr uint32_t R_NONSENSICAL = 1168;
+constexpr uint32_t R_ERR_QUAL = 1169;
+constexpr uint32_t R_ERR_RECORD = 1170;
+constexpr uint32_t R_RECORDS = 1171;
+constexpr uint32_t R_QUAL_POSITIONS = 1172;  // max over records with qualities (reduced with max semantics on host)
+constexpr uint32_t R_FIXED_WORDS = 1184;
+// per contig slot: [0] touched, [1] pileup_too_large, [2..2051) depth histogram, [2051..) bin sums
+constexpr uint32_t COV_TOUCHED = 0, COV_TOO_LARGE = 1, COV_HIST = 2, COV_BINS = 2051;
+
+constexpr int kFacetThreads = 256;
+constexpr uint32_t kTlenPad = 1028, kGcPad = 104, kCigWords = 18 * 32;
+
+struct FacetParams {
+  const uint8_t* d;
+  const uint64_t* rec;
+  uint64_t n_rec;
+  const uint64_t* out_off;
+  const uint64_t* coff;      // file offset of each block (for virtual offsets)
+  uint64_t d_end;
+  uint64_t max_records;      // 0 = all
+  uint64_t gc_seed;
+  int32_t n_ref;
+  uint32_t flags;
+  const uint32_t* ref_len;
+  const uint8_t* cov_enabled;
+  const uint64_t* diff_base; // element offset of each contig's difference array
+  int32_t* diff;
+  const uint32_t* cov_slot;  // word offset of each contig's slot in res
+  uint64_t* res;
+  uint64_t* qual;            // res + quality offset
+  uint32_t qpos_smem;        // positions privatised in shared memory
+  uint32_t qpos_cap;         // positions the global table can hold
+};
+
+__device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
+  extern __shared__ uint32_t sm[];
+  uint32_t* s_qual = sm;
+  uint32_t* s_tlen = s_qual + P.qpos_smem * 94;
+  uint32_t* s_gc = s_tlen + kTlenPad;
+  uint32_t* s_cig = s_gc + kGcPad;
+  const uint32_t n_sm = P.qpos_smem * 94 + kTlenPad + kGcPad + kCigWords;
+  for (uint32_t i = threadIdx.x; i < n_sm; i += blockDim.x) sm[i] = 0;
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps_per_cta = blockDim.x >> 5;
+  const uint64_t n_warps = (uint64_t)gridDim.x * warps_per_cta;
+  const bool do_rec = P.flags & 1u, do_cov = P.flags & 2u;
+  uint32_t acc = 0;          // lane-owned counter (see mask bits below)
+  uint32_t err_qual = 0, err_rec = 0, max_qpos = 0;
+
+  for (uint64_t r = (uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); r < P.n_rec; r += n_warps) {
+    const uint64_t rv = P.rec[r];
+    const uint32_t b = (uint32_t)(rv >> 16), uoff = (uint32_t)(rv & 0xFFFF);
+    const uint8_t* p = P.d + P.out_off[b] + uoff;
+    uint32_t hw = lane < 9 ? ld_u32_unaligned(p + 4 * lane) : 0;
+    const uint32_t bs = __shfl_sync(0xFFFFFFFFu, hw, 0);
+    const int32_t ref = (int32_t)__shfl_sync(0xFFFFFFFFu, hw, 1);
+    const int32_t pos = (int32_t)__shfl_sync(0xFFFFFFFFu, hw, 2);
+    const uint32_t w3 = __shfl_sync(0xFFFFFFFFu, hw, 3);
+    const uint32_t w4 = __shfl_sync(0xFFFFFFFFu, hw, 4);
+    const uint32_t lseq = __shfl_sync(0xFFFFFFFFu, hw, 5);
+    const int32_t nref = (int32_t)__shfl_sync(0xFFFFFFFFu, hw, 6);
+    const int32_t tlen = (int32_t)__shfl_sync(0xFFFFFFFFu, hw, 8);
+    const uint32_t lname = w3 & 255, mapq = (w3 >> 8) & 255, ncig = w4 & 0xFFFF, f = w4 >> 16;
+    const uint64_t need = 32ull + lname + 4ull * ncig + (lseq + 1ull) / 2 + lseq;
+    if (need > bs || ref < -1 || ref >= P.n_ref || nref < -1 || nref >= P.n_ref) { err_rec = 1; continue; }
+    const uint8_t* cig = p + 36 + lname;
+    const uint8_t* seq = cig + 4 * ncig;
+    const uint8_t* qual = seq + (lseq + 1) / 2;
+    const bool in_n = P.max_records == 0 || r < P.max_records;
+    const bool rec_on = do_rec && in_n;
+
+    // ---- CIGAR: kind tallies (general.rs:103-121) and reference span (utils/cigar.rs:6-11)
+    uint32_t span = 0;
+    {
+      const uint32_t which = (f & 0x40) ? 0 : 9;
+      for (uint32_t i = lane; i < ncig; i += 32) {
+        uint32_t op = ld_u32_unaligned(cig + 4 * i);
+        uint32_t k = op & 15;
+        if (k > 8) { err_rec = 1; continue; }
+        if ((0x18D >> k) & 1) span += op >> 4;  // M D N = X
+        if (rec_on) atomicAdd(&s_cig[(which + k) * 32 + lane], 1u);
+      }
+      span = __reduce_add_sync(0xFFFFFFFFu, span);
+    }
+
+    // ---- Coverage scatter (coverage.rs:148-180 behind the query filter)
+    if (do_cov && lane == 0 && ref >= 0 && pos >= 0 && P.cov_enabled[ref]) {
+      const int64_t L = P.ref_len[ref];
+      const int64_t start = (int64_t)pos + 1, end = start + (int64_t)span - 1;
+      if (start <= L && end >= 1) {
+        P.res[P.cov_slot[ref] + COV_TOUCHED] = 1;
+        if (span) {
+          int32_t* df = P.diff + P.diff_base[ref];
+          atomicAdd(df + start, 1);
+          const int64_t e = end < L ? end : L;
+          atomicAdd(df + e + 1, -1);
+          if (end > L) atomicAdd((unsigned long long*)&P.res[R_NONSENSICAL], (unsigned long long)(end - L));
+        }
+      }
+    }
+    if (!rec_on) continue;
+
+    // ---- General counters (general.rs:31-101): bit k of `bits` increments counter k
+    uint32_t bits = 1u;
+    if (f & 0x4) bits |= 1u << 1;
+    if (f & 0x400) bits |= 1u << 2;
+    if (f & 0x100) bits |= 1u << 4;
+    else if (f & 0x800) bits |= 1u << 5;
+    else {
+      bits |= 1u << 3;
+      if (!(f & 0x4)) bits |= 1u << 6;
+      if (f & 0x400) bits |= 1u << 7;
+      if (f & 0x1) {
+        bits |= 1u << 8;
+        if (f & 0x40) bits |= 1u << 9;
+        if (f & 0x80) bits |= 1u << 10;
+        if (!(f & 0x4)) {
+          if (f & 0x2) bits |= 1u << 11;
+          if (f & 0x8) bits |= 1u << 12;
+          else {
+            bits |= 1u << 13;
+            if (ref < 0 || nref < 0) err_rec = 1;  // the reference panics here (general.rs:81-83)
+            else if (ref != nref) {
+              bits |= 1u << 14;
+              if (mapq >= 5) bits |= 1u << 15;     // missing (255) counts (general.rs:88-95)
+            }
+          }
+        }
+      }
+    }
+    // ---- Template length (template_length.rs:79-87): `tlen as usize`, bins 0..=1024
+    if (tlen >= 0 && tlen <= 1024) {
+      bits |= 1u << 16;
+      if (lane == 0) atomicAdd(&s_tlen[tlen], 1u);
+    } else bits |= 1u << 17;
+
+    // ---- GC content (gc_content.rs:38-100)
+    uint32_t gc = 0, at = 0, oth = 0;
+    if (f & (0x400 | 0x100)) bits |= 1u << 19;
+    else if (lseq < 100) bits |= 1u << 20;
+    else {
+      bits |= 1u << 18;
+      uint32_t offset = 0;
+      if (lseq > 100) {
+        const uint64_t voff = (P.coff[b] << 16) | uoff;
+        offset = (uint32_t)(((splitmix64_dev(P.gc_seed ^ voff) >> 32) * (uint64_t)(lseq - 100)) >> 32);
+      }
+#pragma unroll
+      for (uint32_t it = 0; it < 4; ++it) {
+        uint32_t i = it * 32 + lane;
+        if (i < 100) {
+          uint32_t k = offset + i;
+          uint32_t byte = __ldg(seq + (k >> 1));
+          uint32_t code = (k & 1) ? (byte & 15) : (byte >> 4);
+          gc += (code == 2) | (code == 4);
+          at += (code == 1) | (code == 8);
+        }
+      }
+      gc = __reduce_add_sync(0xFFFFFFFFu, gc);
+      at = __reduce_add_sync(0xFFFFFFFFu, at);
+      oth = 100 - gc - at;
+      if (lane == 0) atomicAdd(&s_gc[gc], 1u);  // round(gc/100*100) == gc
+    }
+    uint32_t add = (bits >> lane) & 1u;
+    if (lane == 21) add = gc;
+    if (lane == 22) add = at;
+    if (lane == 23) add = oth;
+    acc += add;
+
+    // ---- Quality scores (quality_scores.rs:37-49; presence rule SURVEY App. D.5)
+    if (lseq) {
+      bool any_real = false, any_bad = false;
+      for (uint32_t i = lane; i < lseq; i += 32) {
+        uint32_t q = __ldg(qual + i);
+        any_real |= q != 0xFF;
+        any_bad |= q > 93;
+      }
+      any_real = __any_sync(0xFFFFFFFFu, any_real);
+      any_bad = __any_sync(0xFFFFFFFFu, any_bad);
+      if (any_real) {
+        if (any_bad) err_qual = 1;
+        else {
+          max_qpos = lseq > max_qpos ? lseq : max_qpos;
+          const uint32_t n_sm_pos = lseq < P.qpos_smem ? lseq : P.qpos_smem;
+          for (uint32_t i = lane; i < n_sm_pos; i += 32) atomicAdd(&s_qual[i * 94 + __ldg(qual + i)], 1u);
+          if (lseq > P.qpos_smem) {
+            if (lseq > P.qpos_cap) err_rec = 1;
+            else
+              for (uint32_t i = P.qpos_smem + lane; i < lseq; i += 32)
+                atomicAdd((unsigned long long*)&P.qual[(uint64_t)i * 94 + __ldg(qual + i)], 1ull);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- flush ----
+  __syncthreads();
+  if (do_rec) {
+    // lane-owned counters: 0..15 general, 16/17 tlen processed/ignored, 18..20 gc records, 21..23 nucleobases
+    if (acc) {
+      uint32_t slot;
+      if (lane < 16) slot = R_GENERAL + lane;
+      else if (lane == 16) slot = R_TLEN_PROCESSED;
+      else if (lane == 17) slot = R_TLEN_IGNORED;
+      else if (lane <= 20) slot = R_GC_REC + (lane - 18);
+      else slot = R_GC_NUC + (lane - 21);
+      if (lane < 24) atomicAdd((unsigned long long*)&P.res[slot], (unsigned long long)acc);
+    }
+    for (uint32_t i = threadIdx.x; i < P.qpos_smem * 94; i += blockDim.x)
+      if (s_qual[i]) atomicAdd((unsigned long long*)&P.qual[i], (unsigned long long)s_qual[i]);
+    for (uint32_t i = threadIdx.x; i < 1025; i += blockDim.x)
+      if (s_tlen[i]) atomicAdd((unsigned long long*)&P.res[R_TLEN_HIST + i], (unsigned long long)s_tlen[i]);
+    for (uint32_t i = threadIdx.x; i < 101; i += blockDim.x)
+      if (s_gc[i]) atomicAdd((unsigned long long*)&P.res[R_GC_HIST + i], (unsigned long long)s_gc[i]);
+    if (threadIdx.x < 18) {
+      uint32_t t = 0;
+      for (uint32_t l = 0; l < 32; ++l) t += s_cig[threadIdx.x * 32 + l];
+      if (t) atomicAdd((unsigned long long*)&P.res[R_CIGAR + threadIdx.x], (unsigned long long)t);
+    }
+    if (max_qpos) atomicMax((unsigned long long*)&P.res[R_QUAL_POSITIONS], (unsigned long long)max_qpos);
+  }
+  if (err_qual) P.res[R_ERR_QUAL] = 1;
+  if (err_rec) P.res[R_ERR_RECORD] = 1;
+}
+
+}  // namespace ngsq

@@ -1,0 +1,388 @@
+// K2 — DEFLATE inflate of independent BGZF blocks (reference: the inflate that
+// noodles-bgzf/miniz_oxide perform under bam::Reader, src/utils/formats/bam.rs:41-44).
+//
+// Shape: a group of G lanes (G = 4/8/16/32; 32 = the warp-per-block form) owns one
+// BGZF block at a time and pulls the next block id from a global atomic queue, so
+// the grid is persistent and block-size skew does not matter.  Within a group:
+//   * lane 0 ("leader") owns the bit reader and decodes Huffman symbols serially
+//     (that part of DEFLATE is inherently bit-serial); literals are stored by the
+//     leader as they are decoded;
+//   * when the leader hits a match it hands (length, distance) to the whole group
+//     through one shuffle and all G lanes copy the LZ77 match;
+//   * dynamic-Huffman tables are built cooperatively by the G lanes into a
+//     per-group shared-memory slab (10-bit literal/length LUT, 8-bit distance LUT,
+//     canonical count/sorted-symbol arrays for the rare longer codes).
+// Several groups share a warp: the symbol loop is the same instruction stream for
+// every group, so G < 32 multiplies the number of concurrently decoding lanes per
+// issued instruction.  This kernel is issue/latency-bound, not HBM-bound.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ngsq {
+
+struct BlockDesc {
+  uint64_t in_off;   // absolute device address of the DEFLATE payload
+  uint64_t out_off;  // offset of this block's first inflated byte
+  uint32_t clen;     // DEFLATE payload length
+  uint32_t isize;    // expected inflated size
+};
+
+enum : uint32_t { kBlkOk = 0, kBlkBadStream = 1, kBlkIsize = 2, kBlkOverrun = 3 };
+
+constexpr int kLLBits = 10;
+constexpr int kDBits = 8;
+constexpr int kInflateThreads = 128;
+
+struct __align__(16) DecSmem {
+  uint16_t ll_lut[1 << kLLBits];  // (sym << 4) | len, 0 = longer than kLLBits / unused
+  uint16_t d_lut[1 << kDBits];
+  uint16_t ll_sorted[288];        // symbols in canonical order (slow path)
+  uint16_t d_sorted[32];
+  uint32_t ll_count[16];
+  uint32_t d_count[16];
+  uint32_t first_code[16];
+  uint32_t offs[16];
+  uint32_t run[16];
+  uint8_t lens[344];              // [0,320) litlen+dist code lengths, [320,339) code-length code lengths
+  uint8_t cl_lut[128];            // (sym << 3) | len
+};
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// Canonical Huffman tables from code lengths, built by the G lanes of a group.
+template <int G>
+__device__ __forceinline__ void build_table(const uint8_t* lens, int n, uint16_t* lut, int lut_bits, uint16_t* sorted,
+                                            uint32_t* count, DecSmem* s, uint32_t gmask, int lig, int lane) {
+  for (int i = lig; i < 16; i += G) { count[i] = 0; s->run[i] = 0; }
+  for (int i = lig; i < (1 << lut_bits) / 2; i += G) reinterpret_cast<uint32_t*>(lut)[i] = 0;
+  __syncwarp(gmask);
+  for (int k = lig; k < n; k += G) {
+    uint32_t l = lens[k];
+    if (l) atomicAdd(&count[l], 1u);
+  }
+  __syncwarp(gmask);
+  if (lig == 0) {
+    uint32_t code = 0, off = 0, prev = 0;
+    for (int l = 1; l <= 15; ++l) {
+      code = (code + prev) << 1;
+      prev = count[l];
+      s->first_code[l] = code;
+      s->offs[l] = off;
+      off += prev;
+    }
+  }
+  __syncwarp(gmask);
+  for (int c = 0; c < n; c += G) {
+    int k = c + lig;
+    uint32_t l = k < n ? lens[k] : 0;
+    uint32_t m = __match_any_sync(gmask, l);
+    uint32_t r = __popc(m & lanemask_lt());
+    uint32_t base = s->run[l];
+    __syncwarp(gmask);
+    if (l && (m >> lane) == 1u) s->run[l] = base + __popc(m);
+    __syncwarp(gmask);
+    if (l) {
+      uint32_t rank = base + r;
+      uint32_t code = s->first_code[l] + rank;
+      sorted[s->offs[l] + rank] = (uint16_t)k;
+      if ((int)l <= lut_bits) {
+        uint32_t rev = __brev(code) >> (32 - l);
+        uint16_t e = (uint16_t)((k << 4) | l);
+        for (uint32_t j = rev; j < (1u << lut_bits); j += (1u << l)) lut[j] = e;
+      }
+    }
+  }
+  __syncwarp(gmask);
+}
+
+// Bit-serial canonical decode for codes longer than the LUT width (leader only).
+__device__ __forceinline__ int slow_decode(uint64_t bb, const uint32_t* count, const uint16_t* sorted, int& len_out) {
+  uint32_t code = 0, first = 0, index = 0;
+  for (int len = 1; len <= 15; ++len) {
+    code |= (uint32_t)(bb & 1);
+    bb >>= 1;
+    uint32_t cnt = count[len];
+    if (code < first + cnt) {
+      len_out = len;
+      return sorted[index + (code - first)];
+    }
+    index += cnt;
+    first = (first + cnt) << 1;
+    code <<= 1;
+  }
+  return -1;
+}
+
+struct BitReader {
+  uint64_t bb;           // bit buffer, LSB first
+  int bc;                // valid bits in bb
+  uint32_t nw;           // prefetched next word
+  const uint32_t* wptr;  // next aligned word to prefetch
+  __device__ __forceinline__ void init(const uint8_t* p) {
+    uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
+    wptr = reinterpret_cast<const uint32_t*>(p - mis);
+    uint32_t w = __ldg(wptr++);
+    bb = (uint64_t)(w >> (8 * mis));
+    bc = 32 - 8 * (int)mis;
+    nw = __ldg(wptr++);
+    refill();
+  }
+  __device__ __forceinline__ void refill() {
+    if (bc <= 32) {
+      bb |= (uint64_t)nw << bc;
+      bc += 32;
+      nw = __ldg(wptr++);
+    }
+  }
+  __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)bb; }
+  __device__ __forceinline__ void drop(int n) { bb >>= n; bc -= n; }
+  __device__ __forceinline__ uint32_t take(int n) {
+    uint32_t v = (uint32_t)bb & ((1u << n) - 1u);
+    drop(n);
+    return v;
+  }
+  // address of the next unread byte once the reader is byte-aligned
+  __device__ __forceinline__ const uint8_t* byte_ptr() const {
+    return reinterpret_cast<const uint8_t*>(wptr) - 4 - (bc >> 3);
+  }
+};
+
+// action word handed from the leader to its group
+//   bits 0-7 match_len-3, 8-22 dist-1, 23-28 literals emitted this phase, 29-31 kind
+enum : uint32_t { kActNone = 0, kActMatch = 1, kActEob = 2, kActErr = 3 };
+constexpr uint32_t kMaxLitRun = 63;
+
+template <int G>
+__global__ void __launch_bounds__(kInflateThreads)
+inflate_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks,
+               uint32_t n_blocks, uint32_t* __restrict__ queue, uint32_t* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int lig = threadIdx.x % G;
+  const int gid = threadIdx.x / G;
+  const uint32_t gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << (lane - lig));
+  const int leader_lane = lane - lig;
+  DecSmem* s = reinterpret_cast<DecSmem*>(smem_raw) + gid;
+
+  BitReader br;
+  br.bb = 0; br.bc = 0; br.nw = 0; br.wptr = nullptr;
+  uint8_t* obase = nullptr;  // output of the current block
+  uint32_t pos = 0, isize = 0, blk = 0;
+  int state = 0;      // 0 need block, 1 need deflate-block header, 2 decoding symbols
+  bool bfinal = false;
+  uint32_t err = 0;
+
+  for (;;) {
+    if (state == 0) {
+      uint32_t b = 0;
+      if (lig == 0) b = atomicAdd(queue, 1u);
+      b = __shfl_sync(gmask, b, leader_lane);
+      if (b >= n_blocks) break;
+      blk = b;
+      BlockDesc d = blocks[b];
+      obase = out + d.out_off;
+      isize = d.isize;
+      pos = 0;
+      err = 0;
+      bfinal = false;
+      if (lig == 0) br.init(reinterpret_cast<const uint8_t*>(d.in_off));
+      state = 1;
+    }
+    if (state == 1) {
+      // ---- deflate block header (leader), tables (group) ----
+      uint32_t hdr = 0;  // bits 0-1 btype, 2 bfinal, 3.. hlit / hdist packed for the group
+      if (lig == 0) {
+        br.refill();
+        uint32_t h = br.take(3);
+        uint32_t btype = h >> 1;
+        hdr = btype | ((h & 1) << 2);
+        if (btype == 2) {
+          br.refill();
+          uint32_t v = br.take(14);
+          uint32_t hlit = (v & 31) + 257, hdist = ((v >> 5) & 31) + 1, hclen = ((v >> 10) & 15) + 4;
+          const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+          uint8_t* cl = s->lens + 320;
+          for (int i = 0; i < 19; ++i) cl[i] = 0;
+          for (uint32_t i = 0; i < hclen; ++i) {
+            br.refill();
+            cl[order[i]] = (uint8_t)br.take(3);
+          }
+          // code-length code: canonical, 7-bit LUT
+          uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, next[8];
+          for (int i = 0; i < 19; ++i) cnt[cl[i]]++;
+          cnt[0] = 0;
+          uint32_t code = 0;
+          for (int l = 1; l <= 7; ++l) { code = (code + cnt[l - 1]) << 1; next[l] = code; }
+          for (int i = 0; i < 32; ++i) reinterpret_cast<uint32_t*>(s->cl_lut)[i] = 0;
+          for (int k = 0; k < 19; ++k) {
+            uint32_t l = cl[k];
+            if (!l) continue;
+            uint32_t c = next[l]++;
+            uint32_t rev = __brev(c) >> (32 - l);
+            for (uint32_t j = rev; j < 128; j += (1u << l)) s->cl_lut[j] = (uint8_t)((k << 3) | l);
+          }
+          uint32_t total = hlit + hdist, i = 0;
+          bool bad = hlit > 286 || hdist > 30;
+          while (i < total && !bad) {
+            br.refill();
+            uint32_t e = s->cl_lut[br.peek32() & 127];
+            uint32_t l = e & 7, sym = e >> 3;
+            if (!l) { bad = true; break; }
+            br.drop(l);
+            if (sym < 16) { s->lens[i++] = (uint8_t)sym; continue; }
+            uint32_t rep, val = 0;
+            if (sym == 16) { if (i == 0) { bad = true; break; } val = s->lens[i - 1]; rep = 3 + br.take(2); }
+            else if (sym == 17) rep = 3 + br.take(3);
+            else rep = 11 + br.take(7);
+            if (i + rep > total) { bad = true; break; }
+            for (uint32_t k = 0; k < rep; ++k) s->lens[i++] = (uint8_t)val;
+          }
+          if (!bad && s->lens[256] == 0) bad = true;
+          hdr |= (hlit << 3) | (hdist << 12);
+          if (bad) hdr = 3;  // reserved btype = error
+        }
+      }
+      hdr = __shfl_sync(gmask, hdr, leader_lane);
+      uint32_t btype = hdr & 3;
+      bfinal = (hdr >> 2) & 1;
+      if (btype == 3) {
+        err = kBlkBadStream;
+      } else if (btype == 0) {
+        // stored block: LEN/NLEN on the next byte boundary, then raw bytes
+        uint32_t len = 0;
+        unsigned long long src = 0;
+        if (lig == 0) {
+          br.drop(br.bc & 7);
+          br.refill();
+          uint32_t v = br.take(16);
+          br.refill();
+          uint32_t nv = br.take(16);
+          if ((v ^ nv) != 0xFFFFu) len = 0xFFFFFFFFu; else len = v;
+          src = (unsigned long long)br.byte_ptr();
+        }
+        len = __shfl_sync(gmask, len, leader_lane);
+        src = __shfl_sync(gmask, src, leader_lane);
+        if (len == 0xFFFFFFFFu) err = kBlkBadStream;
+        else if (pos + len > isize) err = kBlkOverrun;
+        else {
+          const uint8_t* sp = reinterpret_cast<const uint8_t*>(src);
+          for (uint32_t k = lig; k < len; k += G) obase[pos + k] = sp[k];
+          pos += len;
+          if (lig == 0) br.init(sp + len);
+          __syncwarp(gmask);
+        }
+        state = bfinal ? 3 : 1;
+      } else {
+        int n_ll, n_d;
+        if (btype == 1) {
+          for (int k = lig; k < 288; k += G) s->lens[k] = k < 144 ? 8 : k < 256 ? 9 : k < 280 ? 7 : 8;
+          for (int k = lig; k < 32; k += G) s->lens[288 + k] = 5;
+          n_ll = 288; n_d = 32;
+        } else {
+          n_ll = (hdr >> 3) & 511; n_d = (hdr >> 12) & 63;
+        }
+        __syncwarp(gmask);
+        build_table<G>(s->lens, n_ll, s->ll_lut, kLLBits, s->ll_sorted, s->ll_count, s, gmask, lig, lane);
+        build_table<G>(s->lens + n_ll, n_d, s->d_lut, kDBits, s->d_sorted, s->d_count, s, gmask, lig, lane);
+        state = 2;
+      }
+      if (err) state = 3;
+    }
+    if (state == 2) {
+      // ---- phase A: the leader decodes until it needs the group ----
+      uint32_t act = 0;
+      if (lig == 0) {
+        uint32_t nlit = 0, kind = kActNone, mlen = 0, dist = 0;
+        uint8_t* op = obase + pos;
+        uint32_t room = isize - pos;
+        for (;;) {
+          br.refill();
+          uint32_t e = s->ll_lut[br.peek32() & ((1u << kLLBits) - 1u)];
+          int len = e & 15;
+          int sym = e >> 4;
+          if (len == 0) {
+            sym = slow_decode(br.bb, s->ll_count, s->ll_sorted, len);
+            if (sym < 0) { kind = kActErr; break; }
+          }
+          br.drop(len);
+          if (sym < 256) {
+            if (nlit >= room) { kind = kActErr; break; }
+            op[nlit++] = (uint8_t)sym;
+            if (nlit == kMaxLitRun) break;
+            continue;
+          }
+          if (sym == 256) { kind = kActEob; break; }
+          uint32_t idx = sym - 257;
+          if (idx > 28) { kind = kActErr; break; }
+          if (idx < 8) mlen = 3 + idx;
+          else if (idx == 28) mlen = 258;
+          else {
+            uint32_t eb = (idx - 4) >> 2;
+            mlen = 3 + ((4 + (idx & 3)) << eb) + br.take(eb);
+          }
+          br.refill();
+          uint32_t de = s->d_lut[br.peek32() & ((1u << kDBits) - 1u)];
+          int dl = de & 15;
+          int ds = de >> 4;
+          if (dl == 0) {
+            ds = slow_decode(br.bb, s->d_count, s->d_sorted, dl);
+            if (ds < 0) { kind = kActErr; break; }
+          }
+          br.drop(dl);
+          if (ds > 29) { kind = kActErr; break; }
+          if (ds < 4) dist = 1 + ds;
+          else {
+            uint32_t eb = (ds >> 1) - 1;
+            dist = 1 + ((2 + (ds & 1)) << eb) + br.take(eb);
+          }
+          kind = kActMatch;
+          break;
+        }
+        act = (kind << 29) | (nlit << 23);
+        if (kind == kActMatch) act |= (mlen - 3) | ((dist - 1) << 8);
+      }
+      act = __shfl_sync(gmask, act, leader_lane);
+      uint32_t kind = act >> 29;
+      pos += (act >> 23) & 63;
+      if (kind == kActMatch) {
+        uint32_t mlen = (act & 255) + 3, dist = ((act >> 8) & 32767) + 1;
+        if (dist > pos || pos + mlen > isize) {
+          err = kBlkOverrun;
+          state = 3;
+        } else {
+          __syncwarp(gmask);  // leader's literal stores and earlier copies are visible to the group
+          uint8_t* dst = obase + pos;
+          const uint8_t* src = dst - dist;
+          if (dist >= mlen) {
+            for (uint32_t k = lig; k < mlen; k += G) dst[k] = src[k];
+          } else if (dist == 1) {
+            uint8_t v = src[0];
+            for (uint32_t k = lig; k < mlen; k += G) dst[k] = v;
+          } else {
+            for (uint32_t k = lig; k < mlen; k += G) dst[k] = src[k % dist];
+          }
+          pos += mlen;
+        }
+      } else if (kind == kActEob) {
+        state = bfinal ? 3 : 1;
+      } else if (kind == kActErr) {
+        err = kBlkBadStream;
+        state = 3;
+      }
+    }
+    if (state == 3) {
+      // ---- block finished ----
+      if (!err && pos != isize) err = kBlkIsize;
+      if (lig == 0 && err) status[blk] = err;
+      __syncwarp(gmask);
+      state = 0;
+    }
+  }
+}
+
+}  // namespace ngsq

@@ -1,0 +1,191 @@
+"""Test helpers: the oracle (CPU restatement, oracle/ngsqc_oracle.c) through ctypes, and a
+driver that pushes a BAM through the C ABI and collects every integer the engine returns.
+Only tests/, smoke() and bench.py's cpu_baseline may touch oracle/."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+
+_oracle = None
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        lib = C.CDLL(ORACLE_SO)
+        P = C.c_void_p
+        lib.oracle_run.restype = P
+        lib.oracle_run.argtypes = [P, C.c_size_t, P, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
+        lib.oracle_last_error.restype = C.c_char_p
+        lib.oracle_write_json.argtypes = [P, C.c_char_p]
+        lib.oracle_free.argtypes = [P]
+        for name in ["oracle_pass1_records", "oracle_pass2_records", "oracle_inflated_bytes", "oracle_quality_positions"]:
+            getattr(lib, name).restype = C.c_uint64
+            getattr(lib, name).argtypes = [P]
+        lib.oracle_n_ref.restype = C.c_uint32
+        lib.oracle_n_ref.argtypes = [P]
+        lib.oracle_get_general.argtypes = [P, P]
+        lib.oracle_get_tlen.argtypes = [P, P, P, P]
+        lib.oracle_get_gc.argtypes = [P, P, P, P]
+        lib.oracle_get_quality.argtypes = [P, P]
+        lib.oracle_cov_touched.argtypes = [P, C.c_uint32]
+        lib.oracle_cov_nbins.restype = C.c_uint64
+        lib.oracle_cov_nbins.argtypes = [P, C.c_uint32]
+        lib.oracle_get_cov_contig.argtypes = [P, C.c_uint32, P, P, P]
+        lib.oracle_get_cov_dist.argtypes = [P, P, P]
+        lib.oracle_inflate_all.restype = C.c_int64
+        lib.oracle_inflate_all.argtypes = [P, C.c_size_t, P, C.c_size_t]
+        lib.oracle_hist_new.restype = P
+        lib.oracle_hist_new.argtypes = [C.c_uint64]
+        lib.oracle_hist_free.argtypes = [P]
+        lib.oracle_hist_inc_by.argtypes = [P, C.c_uint64, C.c_uint64]
+        lib.oracle_hist_get.restype = C.c_uint64
+        lib.oracle_hist_get.argtypes = [P, C.c_uint64]
+        lib.oracle_hist_len.restype = C.c_uint64
+        lib.oracle_hist_len.argtypes = [P]
+        lib.oracle_hist_mean.restype = C.c_double
+        lib.oracle_hist_mean.argtypes = [P]
+        lib.oracle_hist_percentile.argtypes = [P, C.c_double, C.POINTER(C.c_double)]
+        lib.oracle_hist_sum.restype = C.c_uint64
+        lib.oracle_hist_sum.argtypes = [P]
+        lib.oracle_hist_top_until.restype = C.c_uint64
+        lib.oracle_hist_top_until.argtypes = [P, C.c_uint64]
+        lib.oracle_hist_bottom_until.restype = C.c_uint64
+        lib.oracle_hist_bottom_until.argtypes = [P, C.c_uint64]
+        _oracle = lib
+    return _oracle
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def oracle_ints(bam: np.ndarray, bai: np.ndarray, n_records=0, gc_seed=0, records=True, coverage=True, json_path=None):
+    """Runs the oracle; returns the same integer dict as engine_ints."""
+    lib = oracle_lib()
+    bam = np.ascontiguousarray(bam)
+    bai = np.ascontiguousarray(bai)
+    h = lib.oracle_run(bam.ctypes.data, bam.size, bai.ctypes.data, bai.size, n_records, gc_seed, int(records), int(coverage))
+    if not h:
+        raise OracleError(lib.oracle_last_error().decode())
+    out = {}
+    if records:
+        g = np.zeros(34, dtype=np.uint64)
+        lib.oracle_get_general(h, g.ctypes.data)
+        out["general"] = g
+        th = np.zeros(1025, dtype=np.uint64)
+        p, i = C.c_uint64(0), C.c_uint64(0)
+        lib.oracle_get_tlen(h, th.ctypes.data, C.addressof(p), C.addressof(i))
+        out["tlen_hist"], out["tlen_processed"], out["tlen_ignored"] = th, p.value, i.value
+        gh, nuc, rec = np.zeros(101, dtype=np.uint64), np.zeros(3, dtype=np.uint64), np.zeros(3, dtype=np.uint64)
+        lib.oracle_get_gc(h, gh.ctypes.data, nuc.ctypes.data, rec.ctypes.data)
+        out["gc_hist"], out["gc_nuc"], out["gc_rec"] = gh, nuc, rec
+        nq = lib.oracle_quality_positions(h)
+        q = np.zeros((max(nq, 1), 94), dtype=np.uint64)
+        if nq:
+            lib.oracle_get_quality(h, q.ctypes.data)
+        out["quality"] = q[:nq]
+    if coverage:
+        n_ref = lib.oracle_n_ref(h)
+        cov = {}
+        for c in range(n_ref):
+            if lib.oracle_cov_touched(h, c):
+                nb = lib.oracle_cov_nbins(h, c)
+                hist = np.zeros(2049, dtype=np.uint64)
+                ign = C.c_uint64(0)
+                bins = np.zeros(nb, dtype=np.uint64)
+                lib.oracle_get_cov_contig(h, c, hist.ctypes.data, C.addressof(ign), bins.ctypes.data)
+                cov[c] = {"hist": hist, "too_large": ign.value, "bin_sums": bins}
+        out["coverage"] = cov
+        dist = np.zeros(2049, dtype=np.uint64)
+        ns = C.c_uint64(0)
+        lib.oracle_get_cov_dist(h, dist.ctypes.data, C.addressof(ns))
+        out["nonsensical"] = ns.value
+    out["pass1_records"] = lib.oracle_pass1_records(h)
+    if json_path:
+        lib.oracle_write_json(h, json_path.encode())
+    lib.oracle_free(h)
+    return out
+
+
+def engine_ints(bam: np.ndarray, n_records=0, gc_seed=0, records=True, coverage=True, chunk_bytes=None, lanes=0,
+                crc=True, device=0, shard=None, engine=None):
+    """Pushes a whole BAM (or one shard of it) through the C ABI; returns integers + stats."""
+    from ngs_b200 import ffi, formats
+    flags = (ffi.NGSQ_F_RECORD_FACETS if records else 0) | (ffi.NGSQ_F_COVERAGE if coverage else 0) | (ffi.NGSQ_F_VERIFY_CRC if crc else 0)
+    eng = engine or ffi.Engine(device=device, flags=flags, gc_seed=gc_seed, max_records=n_records, inflate_lanes=lanes)
+    hdr = formats.read_header(eng, bam)
+    names = [n for n, _ in hdr.refs]
+    lens = [l for _, l in hdr.refs]
+    enabled = [1 if formats.is_primary(n) else 0 for n in names]
+    first, end, lo, hi = hdr.first_voffset, 0, hdr.first_voffset >> 16, bam.size
+    if shard is not None:
+        first, end, lo, hi, owned = shard
+        enabled = [e if c in owned else 0 for c, e in enumerate(enabled)]
+    eng.set_references(lens, enabled)
+    eng.set_range(first, end)
+    data = bam[lo:hi]
+    if chunk_bytes is None:
+        eng.submit(np.ascontiguousarray(data), lo)
+    else:
+        o = 0
+        while o < data.size:
+            piece = data[o:o + chunk_bytes]
+            _, n, used = ffi.bgzf_walk(piece, lo + o)
+            if used == 0:
+                piece = data[o:]
+                used = piece.size
+            eng.submit(np.ascontiguousarray(piece[:used]), lo + o)
+            o += used
+    eng.finish()
+    out = collect(eng, lens, enabled, records, coverage)
+    out["refs"] = hdr.refs
+    out["engine"] = eng
+    return out
+
+
+def collect(eng, lens, enabled, records=True, coverage=True):
+    out = {}
+    if records:
+        out["general"] = eng.general()
+        out["tlen_hist"], out["tlen_processed"], out["tlen_ignored"] = eng.tlen()
+        out["gc_hist"], out["gc_nuc"], out["gc_rec"] = eng.gc()
+        out["quality"] = eng.quality()
+    if coverage:
+        cov = {}
+        for c, L in enumerate(lens):
+            if not enabled[c]:
+                continue
+            cc = eng.coverage_contig(c, L)
+            if cc.touched:
+                cov[c] = {"hist": cc.hist, "too_large": cc.pileup_too_large, "bin_sums": cc.bin_sums}
+        out["coverage"] = cov
+        out["nonsensical"] = eng.nonsensical_records()
+    out["stats"] = eng.stats()
+    return out
+
+
+def assert_same_ints(got, want, records=True, coverage=True):
+    if records:
+        for k in ["general", "tlen_hist", "gc_hist", "gc_nuc", "gc_rec"]:
+            np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+        assert got["tlen_processed"] == want["tlen_processed"]
+        assert got["tlen_ignored"] == want["tlen_ignored"]
+        assert got["quality"].shape == want["quality"].shape, (got["quality"].shape, want["quality"].shape)
+        np.testing.assert_array_equal(got["quality"], want["quality"], err_msg="quality")
+    if coverage:
+        assert sorted(got["coverage"]) == sorted(want["coverage"]), "touched contigs differ"
+        for c in want["coverage"]:
+            for k in ["hist", "bin_sums"]:
+                np.testing.assert_array_equal(got["coverage"][c][k], want["coverage"][c][k], err_msg=f"coverage[{c}].{k}")
+            assert got["coverage"][c]["too_large"] == want["coverage"][c]["too_large"]
+        assert got["nonsensical"] == want["nonsensical"]
+
+
+def canonical(obj):
+    """Key-sorted JSON value for comparing results files (map order is random in the reference)."""
+    return json.loads(json.dumps(obj, sort_keys=True))
