@@ -108,8 +108,8 @@ struct ngsq_engine {
   uint32_t h_qpos = 0;
 
   // input / inflate
-  uint8_t* d_comp = nullptr;
-  size_t comp_cap = 0, comp_used = 0;
+  struct CompSeg { uint8_t* ptr; size_t cap, used; };
+  std::vector<CompSeg> comp_segs;  // compressed bytes live in segments: descriptors hold absolute addresses
   uint8_t* d_out = nullptr;
   size_t out_cap = 0;
   uint64_t out_used = 0;
@@ -358,8 +358,10 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
     CUC(cudaMemcpy(e->d_crc_tables, &t, sizeof t, cudaMemcpyHostToDevice));
   }
   if (e->cfg.reserve_compressed) {
-    CUC(cudaMalloc(&e->d_comp, e->cfg.reserve_compressed + 64));
-    e->comp_cap = e->cfg.reserve_compressed;
+    uint8_t* p = nullptr;
+    size_t cap = e->cfg.reserve_compressed + (e->cfg.reserve_compressed >> 6) + 4096;  // room for 16-byte chunk padding
+    CUC(cudaMalloc(&p, cap + 64));
+    e->comp_segs.push_back({p, cap, 0});
   }
   if (e->cfg.reserve_inflated) {
     CUC(cudaMalloc(&e->d_out, e->cfg.reserve_inflated + 64));
@@ -384,10 +386,11 @@ void ngsq_destroy(ngsq_engine* e) {
   for (auto ev : e->copy_events) cudaEventDestroy(ev);
   for (auto& p : e->inflate_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_c, e->ev_d, e->ev_e, e->ev_f}) if (ev) cudaEventDestroy(ev);
-  void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_res, e->d_comp, e->d_out,
+  void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_res, e->d_out,
                   e->d_blocks, e->d_status, e->d_queue, e->d_out_off, e->d_coff, e->d_base, e->d_rec, e->d_first, e->d_landed,
                   e->d_count, e->d_crc, e->d_flags, e->d_crc_tables};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& sg : e->comp_segs) cudaFree(sg.ptr);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
   delete e;
@@ -403,7 +406,16 @@ int ngsq_reset(ngsq_engine* e) {
   for (auto& p : e->inflate_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   e->inflate_events.clear();
   e->h_blocks.clear(); e->h_coff.clear(); e->h_out_off.clear(); e->h_crc.clear();
-  e->comp_used = 0; e->out_used = 0; e->comp_bytes_total = 0; e->n_launches = 0; e->other_launches = 0;
+  // keep the largest compressed segment, drop the rest
+  if (e->comp_segs.size() > 1) {
+    size_t best = 0;
+    for (size_t i = 1; i < e->comp_segs.size(); ++i) if (e->comp_segs[i].cap > e->comp_segs[best].cap) best = i;
+    for (size_t i = 0; i < e->comp_segs.size(); ++i) if (i != best) cudaFree(e->comp_segs[i].ptr);
+    ngsq_engine::CompSeg keep = e->comp_segs[best];
+    e->comp_segs.assign(1, keep);
+  }
+  for (auto& sg : e->comp_segs) sg.used = 0;
+  e->out_used = 0; e->comp_bytes_total = 0; e->n_launches = 0; e->other_launches = 0;
   if (e->d_status && e->blocks_cap) CU(cudaMemsetAsync(e->d_status, 0, (size_t)e->blocks_cap * 4, e->s_comp));
   e->run_started = false; e->finished = false;
   e->h_res.clear(); e->h_qpos = 0;
@@ -514,20 +526,22 @@ int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t fil
   ngsq_bgzf_walk(bgzf, nbytes, file_off, blk.data(), n, &n, &used);
   rc = start_run(e);
   if (rc) return rc;
-  {
-    size_t cap = e->comp_cap;
-    rc = grow(e, e->d_comp, cap, e->comp_used + nbytes, 0, e->s_copy, 64);
-    if (rc) return rc;
-    if (cap != e->comp_cap && e->comp_used) return fail(e, NGSQ_E_ARG, "compressed buffer exhausted mid-run: set ngsq_config.reserve_compressed");
-    e->comp_cap = cap;
+  if (e->comp_segs.empty() || e->comp_segs.back().used + nbytes > e->comp_segs.back().cap) {
+    // a segment that is full stays where it is (in-flight descriptors point into it); open a new one
+    size_t cap = std::max<size_t>(nbytes, e->comp_segs.empty() ? nbytes : (size_t)256 << 20);
+    uint8_t* p = nullptr;
+    cudaError_t r2 = cudaMalloc(&p, cap + 64);
+    if (r2 != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc compressed segment (%zu bytes): %s", cap, cudaGetErrorString(r2));
+    e->comp_segs.push_back({p, cap, 0});
   }
-  uint8_t* dst = e->d_comp + e->comp_used;
+  ngsq_engine::CompSeg& seg = e->comp_segs.back();
+  uint8_t* dst = seg.ptr + seg.used;
   CU(cudaMemcpyAsync(dst, bgzf, nbytes, cudaMemcpyHostToDevice, e->s_copy));
   cudaEvent_t ev;
   CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CU(cudaEventRecord(ev, e->s_copy));
   e->copy_events.push_back(ev);
-  e->comp_used += (nbytes + 15) & ~size_t(15);
+  seg.used += (nbytes + 15) & ~size_t(15);
   e->comp_bytes_total += nbytes;
   uint32_t first_new, n_new;
   rc = append_blocks(e, blk.data(), n, (uint64_t)(uintptr_t)dst, file_off, &first_new, &n_new);

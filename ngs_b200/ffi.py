@@ -292,8 +292,16 @@ class SynthInfo(C.Structure):
 _synth = None
 
 
-def synth_bam(shape: int, n_records: int, seed: int | None = None, level: int = 6, threads: int = 0):
-    """Deterministic synthetic BAM + BAI (tools/bamgen.cpp).  Returns (bam u8 array, bai u8 array, info dict)."""
+def synth_layout(shape: int, n_records: int):
+    """Records per contig and in the unplaced tail of the logical synthetic file."""
+    _load_synth()
+    per = (C.c_uint64 * 64)()
+    n_ref, tail = C.c_uint32(0), C.c_uint64(0)
+    _synth.synth_layout(shape, n_records, per, 64, C.byref(n_ref), C.byref(tail))
+    return [per[i] for i in range(n_ref.value)], tail.value
+
+
+def _load_synth():
     global _synth
     if _synth is None:
         if not os.path.exists(SYNTH_PATH):
@@ -301,12 +309,28 @@ def synth_bam(shape: int, n_records: int, seed: int | None = None, level: int = 
         _synth = C.CDLL(SYNTH_PATH)
         _synth.synth_bam.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.POINTER(SynthInfo)]
+        _synth.synth_bam_subset.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_int,
+                                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(SynthInfo)]
+        _synth.synth_layout.argtypes = [C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_uint64)]
         _synth.synth_free.argtypes = [C.c_void_p]
         _synth.synth_free.restype = None
+
+
+def synth_bam(shape: int, n_records: int, seed: int | None = None, level: int = 6, threads: int = 0,
+              contig_mask: int | None = None, with_tail: bool = True):
+    """Deterministic synthetic BAM + BAI (tools/bamgen.cpp).  Returns (bam u8 array, bai u8 array, info dict).
+    With contig_mask, only those contigs (and the tail if with_tail) of the logical n_records file are written."""
+    global _synth
+    _load_synth()
     if seed is None:
         seed = 0x5EED0001 + shape
     bam, bai, info = C.c_void_p(), C.c_void_p(), SynthInfo()
-    rc = _synth.synth_bam(shape, n_records, seed, level, threads, C.byref(bam), C.byref(bai), C.byref(info))
+    if contig_mask is None:
+        rc = _synth.synth_bam(shape, n_records, seed, level, threads, C.byref(bam), C.byref(bai), C.byref(info))
+    else:
+        rc = _synth.synth_bam_subset(shape, n_records, seed, level, threads, contig_mask, int(with_tail), C.byref(bam),
+                                     C.byref(bai), C.byref(info))
     if rc:
         raise RuntimeError(f"synth_bam failed ({rc})")
     # zero-copy views over the malloc'd buffers; freed when the arrays are garbage collected

@@ -91,6 +91,19 @@ struct Shape {
   uint64_t seed = 0;
   uint32_t read_len = 150;
   uint64_t hot_lo = 0, hot_n = 0;  // hotspot in contig 0: records [hot_lo, hot_lo+hot_n) share one pos
+  // subset generation (one shard of the logical file): global record-index ranges, ascending
+  std::vector<std::pair<uint64_t, uint64_t>> ranges;
+  std::vector<uint64_t> range_base;  // local ordinal of each range's first record
+  uint64_t n_local = 0;
+  uint64_t to_global(uint64_t q) const {
+    size_t k = std::upper_bound(range_base.begin(), range_base.end(), q) - range_base.begin() - 1;
+    return ranges[k].first + (q - range_base[k]);
+  }
+  void set_ranges(std::vector<std::pair<uint64_t, uint64_t>> r) {
+    ranges.clear(); range_base.clear(); n_local = 0;
+    for (auto& x : r) if (x.second > x.first) { ranges.push_back(x); range_base.push_back(n_local); n_local += x.second - x.first; }
+    if (ranges.empty()) { ranges.push_back({0, 0}); range_base.push_back(0); }
+  }
 };
 
 // Everything about a record except its sequence/quality bytes.
@@ -449,6 +462,7 @@ void setup_shape(Shape& sh, int kind, uint64_t n, uint64_t seed) {
   for (size_t c = 0; c < n_ref; ++c) sh.cum[c + 1] = sh.cum[c] + cnt[c];
   if (cnt[0] >= 20000 && kind != 2) { sh.hot_lo = cnt[0] / 3; sh.hot_n = 2600; }
   else if (cnt[0] >= 400) { sh.hot_lo = cnt[0] / 3; sh.hot_n = cnt[0] / 50; }
+  sh.set_ranges({{0, n}});
 }
 
 std::vector<uint8_t> make_header(const Shape& sh) {
@@ -494,14 +508,14 @@ struct BaiRef {
 };
 
 void build(const Shape& sh, int level, int threads, Built& out) {
-  const uint64_t N = sh.n;
-  // pass 1: per-chunk byte totals
+  const uint64_t N = sh.n_local;
+  // pass 1: per-chunk byte totals (chunks of local ordinals)
   uint64_t n_chunks = (N + kChunkRecs - 1) / kChunkRecs;
   std::vector<uint64_t> chunk_off(n_chunks + 1, 0);
   parallel_for(n_chunks, threads, [&](uint64_t ch, int) {
     uint64_t lo = ch * kChunkRecs, hi = std::min(N, lo + kChunkRecs), s = 0;
     Meta m;
-    for (uint64_t i = lo; i < hi; ++i) { make_meta(sh, i, m); s += m.size; }
+    for (uint64_t i = lo; i < hi; ++i) { make_meta(sh, sh.to_global(i), m); s += m.size; }
     chunk_off[ch + 1] = s;
   });
   for (uint64_t ch = 0; ch < n_chunks; ++ch) chunk_off[ch + 1] += chunk_off[ch];
@@ -536,10 +550,11 @@ void build(const Shape& sh, int level, int threads, Built& out) {
     Meta m;
     std::vector<uint8_t> rec;
     while (off < byte1 && i < N) {
-      make_meta(sh, i, m);
+      const uint64_t gi = sh.to_global(i);
+      make_meta(sh, gi, m);
       if (off + m.size > byte0) {
         rec.resize(m.size);
-        make_record(sh, i, m, rec.data());
+        make_record(sh, gi, m, rec.data());
         uint64_t lo = std::max(off, byte0), hi = std::min(off + m.size, byte1);
         memcpy(raw.data() + (lo - byte0), rec.data() + (lo - off), hi - lo);
       }
@@ -585,12 +600,18 @@ void build(const Shape& sh, int level, int threads, Built& out) {
   };
   parallel_for(n_ref, threads, [&](uint64_t c, int) {
     BaiRef& R = refs[c];
-    uint64_t lo = sh.cum[c], hi = sh.cum[c + 1];
-    if (lo == hi) return;
+    uint64_t glo = sh.cum[c], ghi = sh.cum[c + 1];
+    if (glo == ghi) return;
+    // local ordinals of this contig (contigs are included whole or not at all)
+    size_t rk = 0;
+    bool present = false;
+    for (; rk < sh.ranges.size(); ++rk) if (sh.ranges[rk].first <= glo && ghi <= sh.ranges[rk].second) { present = true; break; }
+    if (!present) return;
+    uint64_t lo = sh.range_base[rk] + (glo - sh.ranges[rk].first), hi = lo + (ghi - glo);
     uint64_t ch = lo / kChunkRecs;
     uint64_t i = ch * kChunkRecs, off = chunk_off[ch];
     Meta m;
-    for (; i < lo; ++i) { make_meta(sh, i, m); off += m.size; }
+    for (; i < lo; ++i) { make_meta(sh, sh.to_global(i), m); off += m.size; }
     R.any = true;
     R.beg = voff_of(off);
     R.lin.assign(((uint64_t)sh.contigs[c].len >> 14) + 1, 0);
@@ -604,7 +625,7 @@ void build(const Shape& sh, int level, int threads, Built& out) {
       R.bins[s].second.push_back({save_off, end_off});
     };
     for (; i < hi; ++i) {
-      make_meta(sh, i, m);
+      make_meta(sh, sh.to_global(i), m);
       uint64_t v = voff_of(off);
       if (m.bin != last_bin) { flush(v); last_bin = m.bin; save_off = v; }
       int64_t beg = m.pos, end = (int64_t)m.pos + (m.span ? m.span : 1);
@@ -644,7 +665,7 @@ void build(const Shape& sh, int level, int threads, Built& out) {
     p32((uint32_t)R.lin.size());
     for (uint64_t v : R.lin) p64(v);
   }
-  p64(sh.n_unmapped_tail);
+  p64(sh.ranges.back().second == sh.n && sh.n_local ? sh.n_unmapped_tail : 0);
 }
 
 }  // namespace
@@ -680,6 +701,58 @@ int synth_bam(int shape, uint64_t n_records, uint64_t seed, int level, int threa
     info->n_blocks = b.n_blocks;
     info->n_ref = (uint32_t)sh.contigs.size();
   }
+  return 0;
+}
+
+// One shard of the logical file: only the contigs whose bit is set in contig_mask (whole contigs),
+// plus the unplaced-unmapped tail when with_tail != 0.  Record contents are identical to the
+// corresponding records of the full file (records are pure functions of their global index).
+int synth_bam_subset(int shape, uint64_t n_records, uint64_t seed, int level, int threads, uint64_t contig_mask,
+                     int with_tail, uint8_t** bam, uint8_t** bai, synth_info* info) {
+  if (shape < 0 || shape > 3 || !bam || !bai) return -1;
+  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  if (threads <= 0) threads = 1;
+  Shape sh;
+  setup_shape(sh, shape, n_records, seed);
+  std::vector<std::pair<uint64_t, uint64_t>> r;
+  size_t n_ref = sh.contigs.size();
+  for (size_t c = 0; c < n_ref; ++c)
+    if ((contig_mask >> c) & 1) {
+      if (!r.empty() && r.back().second == sh.cum[c]) r.back().second = sh.cum[c + 1];
+      else r.push_back({sh.cum[c], sh.cum[c + 1]});
+    }
+  if (with_tail) {
+    if (!r.empty() && r.back().second == sh.cum[n_ref]) r.back().second = sh.n;
+    else r.push_back({sh.cum[n_ref], sh.n});
+  }
+  sh.set_ranges(r);
+  Built b;
+  build(sh, level, threads, b);
+  *bam = (uint8_t*)malloc(b.bam.size() ? b.bam.size() : 1);
+  *bai = (uint8_t*)malloc(b.bai.size() ? b.bai.size() : 1);
+  if (!*bam || !*bai) return -2;
+  memcpy(*bam, b.bam.data(), b.bam.size());
+  memcpy(*bai, b.bai.data(), b.bai.size());
+  if (info) {
+    info->n_records = b.n_records;
+    info->inflated_bytes = b.inflated;
+    info->header_bytes = b.header_inflated;
+    info->bam_bytes = b.bam.size();
+    info->bai_bytes = b.bai.size();
+    info->n_blocks = b.n_blocks;
+    info->n_ref = (uint32_t)n_ref;
+  }
+  return 0;
+}
+
+// Record counts per contig (and the tail) of the logical file: lets a planner balance shards.
+int synth_layout(int shape, uint64_t n_records, uint64_t* per_contig, uint32_t cap, uint32_t* n_ref, uint64_t* tail) {
+  Shape sh;
+  setup_shape(sh, shape, n_records, 0);
+  uint32_t n = (uint32_t)sh.contigs.size();
+  if (n_ref) *n_ref = n;
+  for (uint32_t c = 0; c < n && c < cap; ++c) per_contig[c] = sh.cum[c + 1] - sh.cum[c];
+  if (tail) *tail = sh.n_unmapped_tail;
   return 0;
 }
 
