@@ -1,0 +1,256 @@
+// ngs-cuda-qc — host driver of the CUDA `ngs qc` path.  Mirrors the reference's subcommand
+// (src/qc/command.rs): QcArgs (36-102), qc() (109-218), app() (226-421).  Same positional
+// arguments and flags, same checks in the same order, same output file; the two hot loops of
+// app() (305-316 and 350-397) are replaced by one pass of the CUDA engine per GPU.
+//
+//   ngs-cuda-qc qc <BAM> <REFERENCE_GENOME> [-n N] [-o DIR] [-p PREFIX] [--only FACET]
+//               [--cuda-devices 0,1,..] [--cuda-gc-seed S] [--cuda-no-crc] [--cuda-chunk-mb M] [--cuda-perf]
+#include <cstdio>
+#include <cstdlib>
+#include <filesystem>
+#include <iostream>
+#include <optional>
+#include <sstream>
+#include <thread>
+
+#include "bam.hpp"
+#include "facets.hpp"
+
+using namespace ngs;
+
+namespace {
+
+// command.rs:36-102
+struct QcArgs {
+  std::string src;
+  std::string reference_genome;
+  std::optional<std::string> features_gff, reference_fasta, output_prefix, output_directory, only_facet, vaf_file_path;
+  std::optional<uint64_t> num_records;
+  // engine-only knobs (not part of the reference CLI)
+  std::vector<int> devices{0};
+  uint64_t gc_seed = 0;
+  bool verify_crc = true;
+  size_t chunk_mb = 256;
+  bool perf = false;
+};
+
+void info(const std::string& s) { std::cerr << "INFO " << s << "\n"; }
+
+struct ShardRun {
+  ngsq_engine* engine = nullptr;
+  std::string error;
+};
+
+void run_shard(ngsq_engine* e, const MappedFile& file, const Shard& shard, size_t chunk_bytes, std::string* err) {
+  try {
+    if (shard.empty) { check(e, ngsq_finish(e)); return; }
+    uint64_t lo, hi;
+    shard_bytes(shard, file.data(), file.size(), &lo, &hi);
+    check(e, ngsq_set_range(e, shard.first_voffset, shard.end_voffset));
+    // stream whole-block chunks; K1 framing on the host while the previous chunk inflates
+    uint64_t o = lo;
+    while (o < hi) {
+      uint64_t want = std::min<uint64_t>(chunk_bytes, hi - o);
+      uint32_t nb = 0;
+      size_t used = 0;
+      if (ngsq_bgzf_walk(file.data() + o, want, o, nullptr, 0, &nb, &used)) throw std::runtime_error("malformed BGZF framing");
+      if (used == 0) {  // chunk smaller than one block: take the rest
+        if (ngsq_bgzf_walk(file.data() + o, hi - o, o, nullptr, 0, &nb, &used) || used == 0) throw std::runtime_error("truncated BGZF block at end of file");
+      }
+      check(e, ngsq_submit(e, file.data() + o, used, o));
+      o += used;
+    }
+    check(e, ngsq_finish(e));
+  } catch (const std::exception& ex) {
+    *err = ex.what();
+  }
+}
+
+// command.rs:226-421
+int app(const QcArgs& args, const ReferenceGenome& genome, const std::string& output_prefix, const std::string& output_directory) {
+  // open_and_parse(src, IndexCheck::Full): bam.rs:77-123
+  if (args.src.size() < 4 || args.src.substr(args.src.size() - 4) != ".bam")
+    throw std::runtime_error("could not open " + args.src + ": expected a .bam file");
+  MappedFile file(args.src);
+  BaiIndex bai = read_bai(args.src + ".bai");  // pathbuf.rs:59-75: x.bam -> x.bam.bai
+  const uint32_t n_dev = (uint32_t)args.devices.size();
+
+  // facets first (cheap) so `--only` errors surface before any device work
+  FacetSet facets = get_qc_facets(genome, args.only_facet);
+  uint32_t flags = 0;
+  if (!facets.record_based.empty()) flags |= NGSQ_F_RECORD_FACETS;
+  if (!facets.sequence_based.empty()) flags |= NGSQ_F_COVERAGE;
+  if (args.verify_crc) flags |= NGSQ_F_VERIFY_CRC;
+  if (args.num_records && (flags & NGSQ_F_COVERAGE) && (flags & NGSQ_F_RECORD_FACETS))
+    info("-n applies to the first pass; the second pass (Coverage) is skipped on the CUDA engine when -n is given");
+  if (args.num_records) flags &= ~NGSQ_F_COVERAGE;
+  if (args.num_records && n_dev > 1) throw std::runtime_error("-n needs a single device (records are counted in file order)");
+
+  std::vector<ngsq_engine*> engines(n_dev, nullptr);
+  struct Cleanup { std::vector<ngsq_engine*>& v; ~Cleanup() { for (auto* e : v) if (e) ngsq_destroy(e); } } cleanup{engines};
+  for (uint32_t i = 0; i < n_dev; ++i) {
+    ngsq_config cfg{};
+    cfg.struct_size = sizeof cfg;
+    cfg.flags = flags;
+    cfg.gc_seed = args.gc_seed;
+    cfg.max_records = args.num_records.value_or(0);
+    if (ngsq_create(args.devices[i], &cfg, &engines[i])) throw std::runtime_error(std::string("CUDA engine: ") + ngsq_last_error(nullptr));
+  }
+  BamHeader header = read_bam_header(engines[0], file.data(), file.size());
+
+  if (!std::filesystem::exists(output_directory)) std::filesystem::create_directories(output_directory);
+
+  // reference sequence concordance check: command.rs:258-272
+  std::vector<Sequence> supported = get_all_sequences(genome);
+  for (auto& rs : header.reference_sequences) {
+    bool ok = false;
+    for (auto& s : supported) if (s.name == rs.name) { ok = true; break; }
+    if (!ok) throw std::runtime_error("Sequence \"" + rs.name + "\" not found in specified reference genome. Did you set the correct reference genome?");
+  }
+
+  for (auto& f : facets.record_based) info(std::string("  [*] ") + f->name() + ", " + to_string(f->computational_load()));
+  for (auto& f : facets.sequence_based) info(std::string("  [*] ") + f->name() + ", " + to_string(f->computational_load()));
+
+  // shards: contig-aligned file ranges from the BAI
+  std::vector<Shard> shards = plan_shards(header, bai, n_dev, file.size());
+  std::vector<uint32_t> ref_len;
+  for (auto& rs : header.reference_sequences) ref_len.push_back(rs.length);
+  for (uint32_t i = 0; i < n_dev; ++i) {
+    std::vector<uint8_t> enabled(ref_len.size(), 0);
+    for (auto& f : facets.sequence_based)
+      for (uint32_t c : shards[i].contigs)
+        if (f->supports_sequence_name(header.reference_sequences[c].name)) enabled[c] = 1;
+    check(engines[i], ngsq_set_references(engines[i], (uint32_t)ref_len.size(), ref_len.data(), enabled.data()));
+  }
+  if (n_dev > 1) {
+    char id[128];
+    if (ngsq_nccl_unique_id(id)) throw std::runtime_error(std::string("NCCL: ") + ngsq_last_error(nullptr));
+    std::vector<std::thread> ts;
+    std::vector<std::string> errs(n_dev);
+    for (uint32_t i = 0; i < n_dev; ++i)
+      ts.emplace_back([&, i] { if (ngsq_comm_init(engines[i], (int)n_dev, (int)i, id)) errs[i] = ngsq_last_error(engines[i]); });
+    for (auto& t : ts) t.join();
+    for (auto& s : errs) if (!s.empty()) throw std::runtime_error("NCCL: " + s);
+  }
+
+  // the hot path: one thread per GPU
+  info("Starting CUDA pass for QC stats.");
+  {
+    std::vector<std::thread> ts;
+    std::vector<std::string> errs(n_dev);
+    for (uint32_t i = 0; i < n_dev; ++i) ts.emplace_back(run_shard, engines[i], std::cref(file), std::cref(shards[i]), args.chunk_mb << 20, &errs[i]);
+    for (auto& t : ts) t.join();
+    for (auto& s : errs) if (!s.empty()) throw std::runtime_error(s);
+  }
+  if (n_dev > 1) {
+    std::vector<std::thread> ts;
+    std::vector<std::string> errs(n_dev);
+    for (uint32_t i = 0; i < n_dev; ++i) ts.emplace_back([&, i] { if (ngsq_reduce(engines[i], 0)) errs[i] = ngsq_last_error(engines[i]); });
+    for (auto& t : ts) t.join();
+    for (auto& s : errs) if (!s.empty()) throw std::runtime_error("NCCL: " + s);
+  }
+  ngsq_engine* root = engines[0];
+  uint64_t n_records = 0;
+  for (auto* e : engines) { ngsq_stats st; ngsq_get_stats(e, &st); n_records += st.records; }
+  {
+    std::ostringstream os;
+    os << "Processed " << n_records << " records.";
+    info(os.str());
+  }
+
+  // first pass: summarize (command.rs:328-330)
+  for (auto& f : facets.record_based) { f->ingest(root); f->summarize(); }
+  // second pass: per sequence in header order setup -> (process on the device) -> teardown (command.rs:356-396)
+  for (auto& f : facets.sequence_based) f->ingest_global(root);
+  for (uint32_t c = 0; c < header.reference_sequences.size(); ++c) {
+    const ReferenceSequence& seq = header.reference_sequences[c];
+    for (auto& f : facets.sequence_based) {
+      if (!f->supports_sequence_name(seq.name)) continue;
+      f->setup(seq);
+      f->ingest(root, c, seq);
+      f->teardown(seq);
+    }
+  }
+  // finalize: command.rs:406-418
+  info("Aggregating results.");
+  Results results;
+  for (auto& f : facets.record_based) f->aggregate(results);
+  for (auto& f : facets.sequence_based) f->aggregate(results);
+  info("Writing output.");
+  results.write(output_prefix, output_directory);
+
+  if (args.perf) {
+    std::ofstream pf(output_directory + "/" + output_prefix + ".perf.json");
+    pf << "[";
+    for (uint32_t i = 0; i < n_dev; ++i) {
+      ngsq_stats st;
+      ngsq_get_stats(engines[i], &st);
+      pf << (i ? "," : "") << "{\"device\":" << args.devices[i] << ",\"records\":" << st.records << ",\"blocks\":" << st.blocks
+         << ",\"compressed_bytes\":" << st.compressed_bytes << ",\"inflated_bytes\":" << st.inflated_bytes << ",\"ms_inflate\":" << st.ms_inflate
+         << ",\"ms_crc\":" << st.ms_crc << ",\"ms_scan\":" << st.ms_scan << ",\"ms_facets\":" << st.ms_facets << ",\"ms_coverage\":" << st.ms_coverage
+         << ",\"ms_total\":" << st.ms_total << "}";
+    }
+    pf << "]\n";
+  }
+  return 0;
+}
+
+// command.rs:109-218
+int qc(const QcArgs& args) {
+  info("Starting qc command...");
+  auto genome = get_reference_genome(args.reference_genome);
+  if (!genome)
+    throw std::runtime_error("reference genome is not supported: " + args.reference_genome +
+                             ". Did you set the correct reference genome?. Use the `list genomes` subcommand to see supported reference genomes.");
+  if (args.features_gff) throw std::runtime_error("--features-gff (Genomic Features facet) is not available on the CUDA engine; run the CPU `ngs qc` for it");
+  if (args.reference_fasta) throw std::runtime_error("--reference-fasta (Edits facet) is not available on the CUDA engine; run the CPU `ngs qc` for it");
+  std::string prefix = args.output_prefix.value_or(std::filesystem::path(args.src).filename().string());
+  std::string outdir = args.output_directory.value_or(std::filesystem::current_path().string());
+  return app(args, *genome, prefix, outdir);
+}
+
+void usage() {
+  std::cerr << "usage: ngs-cuda-qc qc <BAM> <REFERENCE_GENOME> [-n N] [-o DIR] [-p PREFIX] [--only FACET]\n"
+               "                  [--cuda-devices 0,1,..] [--cuda-gc-seed S] [--cuda-no-crc] [--cuda-chunk-mb M] [--cuda-perf]\n";
+}
+
+}  // namespace
+
+extern "C" int ngs_cuda_qc_main(int argc, char** argv) {
+  try {
+    QcArgs a;
+    std::vector<std::string> pos;
+    int i = 1;
+    if (i < argc && std::string(argv[i]) == "qc") ++i;
+    for (; i < argc; ++i) {
+      std::string s = argv[i];
+      auto val = [&]() -> std::string { if (i + 1 >= argc) throw std::runtime_error("missing value for " + s); return argv[++i]; };
+      if (s == "-n" || s == "--num-records") a.num_records = std::stoull(val());
+      else if (s == "-o" || s == "--output-directory") a.output_directory = val();
+      else if (s == "-p" || s == "--output-prefix") a.output_prefix = val();
+      else if (s == "-f" || s == "--features-gff") a.features_gff = val();
+      else if (s == "-r" || s == "--reference-fasta") a.reference_fasta = val();
+      else if (s == "--only") a.only_facet = val();
+      else if (s == "--vaf-file") a.vaf_file_path = val();
+      else if (s == "--cuda-devices") { a.devices.clear(); std::stringstream ss(val()); std::string t; while (std::getline(ss, t, ',')) a.devices.push_back(std::stoi(t)); }
+      else if (s == "--cuda-gc-seed") a.gc_seed = std::stoull(val(), nullptr, 0);
+      else if (s == "--cuda-no-crc") a.verify_crc = false;
+      else if (s == "--cuda-chunk-mb") a.chunk_mb = std::stoull(val());
+      else if (s == "--cuda-perf") a.perf = true;
+      else if (s == "-h" || s == "--help") { usage(); return 0; }
+      else if (!s.empty() && s[0] == '-' && s != "-") throw std::runtime_error("unknown flag " + s);
+      else pos.push_back(s);
+    }
+    if (pos.size() != 2 || a.devices.empty()) { usage(); return 2; }
+    a.src = pos[0];
+    a.reference_genome = pos[1];
+    return qc(a);
+  } catch (const std::exception& ex) {
+    std::cerr << "Error: " << ex.what() << "\n";
+    return 1;
+  }
+}
+
+#ifndef NGS_CUDA_QC_NO_MAIN
+int main(int argc, char** argv) { return ngs_cuda_qc_main(argc, argv); }
+#endif
