@@ -215,7 +215,7 @@ def main():
     enabled = [1 if (formats.is_primary(nm) and c in parts[rank]) else 0 for c, nm in enumerate(names)]
     eng.set_references(lens, enabled)
     eng.set_range(hdr.first_voffset, 0)
-    d_comp = torch.empty(C_bytes + 64, dtype=torch.uint8, device=dev)
+    d_comp = torch.empty(C_bytes + 512, dtype=torch.uint8, device=dev)
     d_comp[:C_bytes].copy_(torch.from_numpy(pinned))
     torch.cuda.synchronize()
 

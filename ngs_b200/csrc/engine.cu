@@ -360,7 +360,7 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   if (e->cfg.reserve_compressed) {
     uint8_t* p = nullptr;
     size_t cap = e->cfg.reserve_compressed + (e->cfg.reserve_compressed >> 6) + 4096;  // room for 16-byte chunk padding
-    CUC(cudaMalloc(&p, cap + 64));
+    CUC(cudaMalloc(&p, cap + 512));
     e->comp_segs.push_back({p, cap, 0});
   }
   if (e->cfg.reserve_inflated) {
@@ -530,7 +530,7 @@ int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t fil
     // a segment that is full stays where it is (in-flight descriptors point into it); open a new one
     size_t cap = std::max<size_t>(nbytes, e->comp_segs.empty() ? nbytes : (size_t)256 << 20);
     uint8_t* p = nullptr;
-    cudaError_t r2 = cudaMalloc(&p, cap + 64);
+    cudaError_t r2 = cudaMalloc(&p, cap + 512);
     if (r2 != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc compressed segment (%zu bytes): %s", cap, cudaGetErrorString(r2));
     e->comp_segs.push_back({p, cap, 0});
   }
@@ -924,7 +924,7 @@ int ngsq_inflate_to_host(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uin
   uint32_t *d_st = nullptr, *d_q = nullptr;
   std::vector<BlockDesc> hb;
   uint64_t total = 0;
-  CU(cudaMalloc(&d_in, used + 64));
+  CU(cudaMalloc(&d_in, used + 512));
   for (auto& b : blk) {
     if (b.csize < b.hdr_len + 8 || b.isize > 65536) { cudaFree(d_in); return fail(e, NGSQ_E_BAD_BLOCK, "malformed BGZF block"); }
     if (!b.isize) continue;

@@ -44,6 +44,10 @@ struct __align__(16) DecSmem {
   uint32_t first_code[16];
   uint32_t offs[16];
   uint32_t run[16];
+  uint16_t ll_lim[16], d_lim[16];  // slow path: (first_code[l] + count[l]) << (15 - l)
+  int16_t ll_base[16], d_base[16]; // slow path: offs[l] - first_code[l]
+  uint32_t tok_pl[8];              // queued matches: pos | (len - 3) << 16
+  uint32_t tok_d[8];               //                 dist | dependent << 31
   uint8_t lens[344];              // [0,320) litlen+dist code lengths, [320,339) code-length code lengths
   uint8_t cl_lut[128];            // (sym << 3) | len
 };
@@ -57,7 +61,8 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 // Canonical Huffman tables from code lengths, built by the G lanes of a group.
 template <int G>
 __device__ __forceinline__ void build_table(const uint8_t* lens, int n, uint16_t* lut, int lut_bits, uint16_t* sorted,
-                                            uint32_t* count, DecSmem* s, uint32_t gmask, int lig, int lane) {
+                                            uint32_t* count, uint16_t* lim, int16_t* base, DecSmem* s, uint32_t gmask,
+                                            int lig, int lane) {
   for (int i = lig; i < 16; i += G) { count[i] = 0; s->run[i] = 0; }
   for (int i = lig; i < (1 << lut_bits) / 2; i += G) reinterpret_cast<uint32_t*>(lut)[i] = 0;
   __syncwarp(gmask);
@@ -73,6 +78,8 @@ __device__ __forceinline__ void build_table(const uint8_t* lens, int n, uint16_t
       prev = count[l];
       s->first_code[l] = code;
       s->offs[l] = off;
+      lim[l] = (uint16_t)min((code + prev) << (15 - l), 0xFFFFu);
+      base[l] = (int16_t)((int)off - (int)code);
       off += prev;
     }
   }
@@ -100,28 +107,27 @@ __device__ __forceinline__ void build_table(const uint8_t* lens, int n, uint16_t
   __syncwarp(gmask);
 }
 
-// Bit-serial canonical decode for codes longer than the LUT width (leader only).
-__device__ __forceinline__ int slow_decode(uint64_t bb, const uint32_t* count, const uint16_t* sorted, int& len_out) {
-  uint32_t code = 0, first = 0, index = 0;
-  for (int len = 1; len <= 15; ++len) {
-    code |= (uint32_t)(bb & 1);
-    bb >>= 1;
-    uint32_t cnt = count[len];
-    if (code < first + cnt) {
-      len_out = len;
-      return sorted[index + (code - first)];
+// Canonical decode for codes longer than the LUT width (leader only): left-align the next 15 bits
+// MSB-first; canonical codes are ordered, so the first length whose limit exceeds them is the length.
+template <int LUT_BITS>
+__device__ __forceinline__ int slow_decode(uint32_t bits, const uint16_t* lim, const int16_t* base, const uint16_t* sorted,
+                                           int& len_out) {
+  const uint32_t x = __brev(bits) >> 17;
+#pragma unroll
+  for (int l = LUT_BITS + 1; l <= 15; ++l) {
+    if (x < lim[l]) {
+      len_out = l;
+      return sorted[(int)(x >> (15 - l)) + base[l]];
     }
-    index += cnt;
-    first = (first + cnt) << 1;
-    code <<= 1;
   }
+  len_out = 0;
   return -1;
 }
 
 struct BitReader {
   uint64_t bb;           // bit buffer, LSB first
   int bc;                // valid bits in bb
-  uint32_t nw;           // prefetched next word
+  uint32_t nw0, nw1;     // two prefetched words: an L1 miss on the input stream has ~64 bits of slack
   const uint32_t* wptr;  // next aligned word to prefetch
   __device__ __forceinline__ void init(const uint8_t* p) {
     uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
@@ -129,14 +135,16 @@ struct BitReader {
     uint32_t w = __ldg(wptr++);
     bb = (uint64_t)(w >> (8 * mis));
     bc = 32 - 8 * (int)mis;
-    nw = __ldg(wptr++);
+    nw0 = __ldg(wptr++);
+    nw1 = __ldg(wptr++);
     refill();
   }
   __device__ __forceinline__ void refill() {
     if (bc <= 32) {
-      bb |= (uint64_t)nw << bc;
+      bb |= (uint64_t)nw0 << bc;
       bc += 32;
-      nw = __ldg(wptr++);
+      nw0 = nw1;
+      nw1 = __ldg(wptr++);
     }
   }
   __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)bb; }
@@ -148,15 +156,46 @@ struct BitReader {
   }
   // address of the next unread byte once the reader is byte-aligned
   __device__ __forceinline__ const uint8_t* byte_ptr() const {
-    return reinterpret_cast<const uint8_t*>(wptr) - 4 - (bc >> 3);
+    return reinterpret_cast<const uint8_t*>(wptr) - 8 - (bc >> 3);
   }
 };
 
-// action word handed from the leader to its group
-//   bits 0-7 match_len-3, 8-22 dist-1, 23-28 literals emitted this phase, 29-31 kind
-enum : uint32_t { kActNone = 0, kActMatch = 1, kActEob = 2, kActErr = 3 };
-constexpr uint32_t kMaxLitRun = 63;
+constexpr int kTokens = 8;       // match tokens a leader may queue per batch
+constexpr int kBatchIters = 40;  // symbols a leader may decode per batch
+enum : int { ST_BLOCK = 0, ST_HEADER = 1, ST_DECODE = 2, ST_FINISH = 3, ST_DONE = 4 };
 
+template <int G>
+struct LeaderMask;
+template <> struct LeaderMask<32> { static constexpr uint32_t v = 0x00000001u; };
+template <> struct LeaderMask<16> { static constexpr uint32_t v = 0x00010001u; };
+template <> struct LeaderMask<8> { static constexpr uint32_t v = 0x01010101u; };
+template <> struct LeaderMask<4> { static constexpr uint32_t v = 0x11111111u; };
+template <> struct LeaderMask<2> { static constexpr uint32_t v = 0x55555555u; };
+
+// one lane copies one LZ77 match; sources never include bytes of this match (periodic extension)
+__device__ __forceinline__ void lane_copy(uint8_t* dst, uint32_t mlen, uint32_t dist) {
+  const uint8_t* src = dst - dist;
+  if (dist >= mlen) {
+    uint32_t k = 0;
+    for (; k + 4 <= mlen; k += 4) {
+      uint8_t a = src[k], b = src[k + 1], c = src[k + 2], d = src[k + 3];
+      dst[k] = a; dst[k + 1] = b; dst[k + 2] = c; dst[k + 3] = d;
+    }
+    for (; k < mlen; ++k) dst[k] = src[k];
+  } else if (dist == 1) {
+    uint8_t v = src[0];
+    for (uint32_t k = 0; k < mlen; ++k) dst[k] = v;
+  } else {
+    uint32_t sidx = 0;
+    for (uint32_t k = 0; k < mlen; ++k) {
+      dst[k] = src[sidx];
+      sidx = sidx + 1 == dist ? 0 : sidx + 1;
+    }
+  }
+}
+
+// Persistent kernel: every warp runs one flat state machine; all 32 lanes reconverge at the loop
+// top each iteration, so the 32/G leaders of a warp execute the symbol loop in lock step.
 template <int G>
 __global__ void __launch_bounds__(kInflateThreads)
 inflate_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks,
@@ -167,33 +206,40 @@ inflate_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks,
   const int gid = threadIdx.x / G;
   const uint32_t gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << (lane - lig));
   const int leader_lane = lane - lig;
+  constexpr uint32_t kLeaders = LeaderMask<G>::v;
   DecSmem* s = reinterpret_cast<DecSmem*>(smem_raw) + gid;
 
   BitReader br;
-  br.bb = 0; br.bc = 0; br.nw = 0; br.wptr = nullptr;
+  br.bb = 0; br.bc = 0; br.nw0 = 0; br.nw1 = 0; br.wptr = nullptr;
   uint8_t* obase = nullptr;  // output of the current block
+  const uint8_t* in_end = nullptr;  // end of the block's DEFLATE payload (leader)
   uint32_t pos = 0, isize = 0, blk = 0;
-  int state = 0;      // 0 need block, 1 need deflate-block header, 2 decoding symbols
+  int state = ST_BLOCK;
   bool bfinal = false;
   uint32_t err = 0;
 
   for (;;) {
-    if (state == 0) {
+    __syncwarp();
+    if (state == ST_BLOCK) {
       uint32_t b = 0;
       if (lig == 0) b = atomicAdd(queue, 1u);
       b = __shfl_sync(gmask, b, leader_lane);
-      if (b >= n_blocks) break;
-      blk = b;
-      BlockDesc d = blocks[b];
-      obase = out + d.out_off;
-      isize = d.isize;
-      pos = 0;
-      err = 0;
-      bfinal = false;
-      if (lig == 0) br.init(reinterpret_cast<const uint8_t*>(d.in_off));
-      state = 1;
+      if (b >= n_blocks) {
+        state = ST_DONE;
+      } else {
+        blk = b;
+        BlockDesc d = blocks[b];
+        obase = out + d.out_off;
+        isize = d.isize;
+        pos = 0;
+        err = 0;
+        bfinal = false;
+        in_end = reinterpret_cast<const uint8_t*>(d.in_off) + d.clen;
+        if (lig == 0) br.init(reinterpret_cast<const uint8_t*>(d.in_off));
+        state = ST_HEADER;
+      }
     }
-    if (state == 1) {
+    if (state == ST_HEADER) {
       // ---- deflate block header (leader), tables (group) ----
       uint32_t hdr = 0;  // bits 0-1 btype, 2 bfinal, 3.. hlit / hdist packed for the group
       if (lig == 0) {
@@ -252,6 +298,7 @@ inflate_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks,
       bfinal = (hdr >> 2) & 1;
       if (btype == 3) {
         err = kBlkBadStream;
+        state = ST_FINISH;
       } else if (btype == 0) {
         // stored block: LEN/NLEN on the next byte boundary, then raw bytes
         uint32_t len = 0;
@@ -276,7 +323,7 @@ inflate_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks,
           if (lig == 0) br.init(sp + len);
           __syncwarp(gmask);
         }
-        state = bfinal ? 3 : 1;
+        state = (bfinal || err) ? ST_FINISH : ST_HEADER;
       } else {
         int n_ll, n_d;
         if (btype == 1) {
@@ -287,101 +334,121 @@ inflate_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks,
           n_ll = (hdr >> 3) & 511; n_d = (hdr >> 12) & 63;
         }
         __syncwarp(gmask);
-        build_table<G>(s->lens, n_ll, s->ll_lut, kLLBits, s->ll_sorted, s->ll_count, s, gmask, lig, lane);
-        build_table<G>(s->lens + n_ll, n_d, s->d_lut, kDBits, s->d_sorted, s->d_count, s, gmask, lig, lane);
-        state = 2;
+        build_table<G>(s->lens, n_ll, s->ll_lut, kLLBits, s->ll_sorted, s->ll_count, s->ll_lim, s->ll_base, s, gmask, lig, lane);
+        build_table<G>(s->lens + n_ll, n_d, s->d_lut, kDBits, s->d_sorted, s->d_count, s->d_lim, s->d_base, s, gmask, lig, lane);
+        state = ST_DECODE;
       }
-      if (err) state = 3;
     }
-    if (state == 2) {
-      // ---- phase A: the leader decodes until it needs the group ----
-      uint32_t act = 0;
-      if (lig == 0) {
-        uint32_t nlit = 0, kind = kActNone, mlen = 0, dist = 0;
-        uint8_t* op = obase + pos;
-        uint32_t room = isize - pos;
-        for (;;) {
+    __syncwarp();
+    // ---- phase A: every leader decodes up to kBatchIters symbols in lock step; literals are stored
+    // at once, matches are queued as tokens (at most kTokens) ----
+    uint32_t res = 0;  // bits 0-16 new pos, 17-20 tokens queued, 21-22 end kind (1 EOB, 2 bad stream, 3 overrun)
+    if (lig == 0) {
+      bool active = state == ST_DECODE;
+      uint32_t p = pos, ntok = 0, endk = 0, first_dst = 0;
+      for (int it = 0; it < kBatchIters; ++it) {
+        if (active) {
           br.refill();
           uint32_t e = s->ll_lut[br.peek32() & ((1u << kLLBits) - 1u)];
           int len = e & 15;
           int sym = e >> 4;
-          if (len == 0) {
-            sym = slow_decode(br.bb, s->ll_count, s->ll_sorted, len);
-            if (sym < 0) { kind = kActErr; break; }
-          }
-          br.drop(len);
-          if (sym < 256) {
-            if (nlit >= room) { kind = kActErr; break; }
-            op[nlit++] = (uint8_t)sym;
-            if (nlit == kMaxLitRun) break;
-            continue;
-          }
-          if (sym == 256) { kind = kActEob; break; }
-          uint32_t idx = sym - 257;
-          if (idx > 28) { kind = kActErr; break; }
-          if (idx < 8) mlen = 3 + idx;
-          else if (idx == 28) mlen = 258;
+          if (len == 0) sym = slow_decode<kLLBits>(br.peek32(), s->ll_lim, s->ll_base, s->ll_sorted, len);
+          if (sym < 0) { endk = 2; active = false; }
           else {
-            uint32_t eb = (idx - 4) >> 2;
-            mlen = 3 + ((4 + (idx & 3)) << eb) + br.take(eb);
+            br.drop(len);
+            if (sym < 256) {
+              if (p >= isize) { endk = 3; active = false; }
+              else obase[p++] = (uint8_t)sym;
+            } else if (sym == 256) {
+              endk = 1; active = false;
+            } else {
+              uint32_t idx = sym - 257, mlen, dist = 0;
+              if (idx < 8) mlen = 3 + idx;
+              else if (idx >= 28) mlen = 258;
+              else {
+                uint32_t eb = (idx - 4) >> 2;
+                mlen = 3 + ((4 + (idx & 3)) << eb) + br.take(eb);
+              }
+              br.refill();
+              uint32_t de = s->d_lut[br.peek32() & ((1u << kDBits) - 1u)];
+              int dl = de & 15;
+              int ds = de >> 4;
+              if (dl == 0) ds = slow_decode<kDBits>(br.peek32(), s->d_lim, s->d_base, s->d_sorted, dl);
+              if (ds < 0 || ds > 29 || idx > 28) { endk = 2; active = false; }
+              else {
+                br.drop(dl);
+                if (ds < 4) dist = 1 + ds;
+                else {
+                  uint32_t eb = (ds >> 1) - 1;
+                  dist = 1 + ((2 + (ds & 1)) << eb) + br.take(eb);
+                }
+                if (dist > p || p + mlen > isize) { endk = 3; active = false; }
+                else {
+                  // a token depends on this batch when its source reaches into an earlier queued match
+                  uint32_t dep = (ntok && p - dist + mlen > first_dst) ? 0x80000000u : 0u;
+                  if (!ntok) first_dst = p;
+                  s->tok_pl[ntok] = p | ((mlen - 3) << 16);
+                  s->tok_d[ntok] = dist | dep;
+                  ++ntok;
+                  p += mlen;
+                  if (ntok == kTokens) active = false;
+                }
+              }
+            }
           }
-          br.refill();
-          uint32_t de = s->d_lut[br.peek32() & ((1u << kDBits) - 1u)];
-          int dl = de & 15;
-          int ds = de >> 4;
-          if (dl == 0) {
-            ds = slow_decode(br.bb, s->d_count, s->d_sorted, dl);
-            if (ds < 0) { kind = kActErr; break; }
-          }
-          br.drop(dl);
-          if (ds > 29) { kind = kActErr; break; }
-          if (ds < 4) dist = 1 + ds;
-          else {
-            uint32_t eb = (ds >> 1) - 1;
-            dist = 1 + ((2 + (ds & 1)) << eb) + br.take(eb);
-          }
-          kind = kActMatch;
-          break;
         }
-        act = (kind << 29) | (nlit << 23);
-        if (kind == kActMatch) act |= (mlen - 3) | ((dist - 1) << 8);
+        if (!__any_sync(kLeaders, active)) break;
       }
-      act = __shfl_sync(gmask, act, leader_lane);
-      uint32_t kind = act >> 29;
-      pos += (act >> 23) & 63;
-      if (kind == kActMatch) {
-        uint32_t mlen = (act & 255) + 3, dist = ((act >> 8) & 32767) + 1;
-        if (dist > pos || pos + mlen > isize) {
-          err = kBlkOverrun;
-          state = 3;
-        } else {
-          __syncwarp(gmask);  // leader's literal stores and earlier copies are visible to the group
-          uint8_t* dst = obase + pos;
-          const uint8_t* src = dst - dist;
-          if (dist >= mlen) {
+      // a malformed stream must not run away over the input: the reader may be at most its prefetch ahead
+      if (state == ST_DECODE && !endk && reinterpret_cast<const uint8_t*>(br.wptr) > in_end + 24) endk = 2;
+      res = p | (ntok << 17) | (endk << 21);
+    }
+    res = __shfl_sync(gmask, res, leader_lane);
+    __syncwarp();  // literal stores and tokens are visible to every lane
+    // ---- phase B: copies.  B1: one lane per independent token; B2: dependent tokens in order ----
+    {
+      const uint32_t ntok = (res >> 17) & 15;
+      for (uint32_t j = lig; j < ntok; j += G) {
+        uint32_t d = s->tok_d[j];
+        if (!(d & 0x80000000u)) {
+          uint32_t pl = s->tok_pl[j];
+          lane_copy(obase + (pl & 0xFFFF), (pl >> 16) + 3, d);
+        }
+      }
+      __syncwarp();
+      for (uint32_t j = 1; j < ntok; ++j) {
+        uint32_t d = s->tok_d[j];
+        if (d & 0x80000000u) {
+          d &= 0x7FFFFFFFu;
+          uint32_t pl = s->tok_pl[j];
+          uint32_t mlen = (pl >> 16) + 3;
+          uint8_t* dst = obase + (pl & 0xFFFF);
+          const uint8_t* src = dst - d;
+          if (d >= mlen) {
             for (uint32_t k = lig; k < mlen; k += G) dst[k] = src[k];
-          } else if (dist == 1) {
+          } else if (d == 1) {
             uint8_t v = src[0];
             for (uint32_t k = lig; k < mlen; k += G) dst[k] = v;
           } else {
-            for (uint32_t k = lig; k < mlen; k += G) dst[k] = src[k % dist];
+            for (uint32_t k = lig; k < mlen; k += G) dst[k] = src[k % d];
           }
-          pos += mlen;
+          __syncwarp(gmask);
         }
-      } else if (kind == kActEob) {
-        state = bfinal ? 3 : 1;
-      } else if (kind == kActErr) {
-        err = kBlkBadStream;
-        state = 3;
+      }
+      if (state == ST_DECODE) {
+        pos = res & 0x1FFFF;
+        uint32_t endk = (res >> 21) & 3;
+        if (endk == 1) state = bfinal ? ST_FINISH : ST_HEADER;
+        else if (endk == 2) { err = kBlkBadStream; state = ST_FINISH; }
+        else if (endk == 3) { err = kBlkOverrun; state = ST_FINISH; }
       }
     }
-    if (state == 3) {
-      // ---- block finished ----
+    if (state == ST_FINISH) {
       if (!err && pos != isize) err = kBlkIsize;
       if (lig == 0 && err) status[blk] = err;
-      __syncwarp(gmask);
-      state = 0;
+      state = ST_BLOCK;
     }
+    if (__all_sync(0xFFFFFFFFu, state == ST_DONE)) break;
   }
 }
 

@@ -189,3 +189,18 @@ def assert_same_ints(got, want, records=True, coverage=True):
 def canonical(obj):
     """Key-sorted JSON value for comparing results files (map order is random in the reference)."""
     return json.loads(json.dumps(obj, sort_keys=True))
+
+
+def canonical_results(path_or_obj):
+    """Parsed, key-sorted results JSON; genome_covered_by values pass through float32 (they are f32 in
+    the reference, coverage.rs:282, and writers may print them with different digit counts)."""
+    obj = json.load(open(path_or_obj)) if isinstance(path_or_obj, str) else path_or_obj
+    cov = obj.get("coverage")
+    if cov and cov.get("genome_covered_by"):
+        cov["genome_covered_by"] = {k: (None if v is None else float(np.float32(v))) for k, v in cov["genome_covered_by"].items()}
+    return json.loads(json.dumps(obj, sort_keys=True))
+
+
+def results_digest(path_or_obj) -> str:
+    import hashlib
+    return hashlib.sha256(json.dumps(canonical_results(path_or_obj), sort_keys=True).encode()).hexdigest()

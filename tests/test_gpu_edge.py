@@ -1,0 +1,175 @@
+"""Edge shapes the reference's decoder accepts or rejects (SURVEY section 4 list): stored / fixed-Huffman /
+empty / 64 KiB blocks, extra gzip subfields, records straddling tiny blocks, empty files, odd records;
+and the error paths (corrupt DEFLATE, CRC, ISIZE, quality > 93, CIGAR op > 8, truncation)."""
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from bamutil import EOF_BLOCK, as_u8, bgzf_block, header_bytes, rec, record, write_bam
+from helpers import assert_same_ints, engine_ints, oracle_ints
+
+pytestmark = pytest.mark.gpu
+REFS = [("chr1", 100000), ("chr2", 60000), ("chrM", 16569)]
+
+
+def _records(n=400, seed=1, long_names=False):
+    rng = np.random.default_rng(seed)
+    out = []
+    for ref in (0, 1, 2):
+        pos = 0
+        for i in range(n // 3):
+            pos += int(rng.integers(0, 200))
+            L = int(rng.integers(20, 160))
+            cig = rng.choice([f"{L}M", f"5S{L-5}M", f"{L-10}M3I7M", f"10M5D{L-10}M", f"{L//2}M300N{L-L//2}M", f"4H{L}M", f"{L}="])
+            flag = int(rng.choice([0x63, 0x93, 0x53, 0xA3, 0x400 | 0x63, 0x100 | 0x93, 0x800 | 0x63, 0x41, 0x0, 0x49]))
+            seq = "".join(rng.choice(list("ACGTN"), size=L, p=[0.27, 0.22, 0.22, 0.27, 0.02]))
+            qual = None if i % 37 == 0 else rng.integers(0, 94, size=L).tolist()
+            nref = ref if rng.random() < 0.9 else int(rng.integers(0, 3))
+            name = ("read_with_a_rather_long_name_" * 6 + str(i))[:200] if long_names and i % 5 == 0 else f"r{ref}_{i}"
+            out.append(rec(name=name, flag=flag, ref=ref, pos=pos, mapq=int(rng.choice([0, 3, 5, 30, 60, 255])), cigar=cig,
+                           next_ref=nref, next_pos=pos + 100, tlen=int(rng.integers(-1200, 1200)), seq=seq, qual=qual,
+                           aux=b"NMC\x01" if i % 2 else b""))
+    out += [rec(name=f"u{i}", flag=0x4 | 0x1 | 0x8 | 0x40, seq="ACGT" * 10, qual=[20] * 40) for i in range(7)]
+    out += [rec(name="empty", flag=0x4)]
+    return out
+
+
+def _check(bam, bai, **kw):
+    b, i = as_u8(bam), as_u8(bai)
+    want = oracle_ints(b, i, gc_seed=3)
+    got = engine_ints(b, gc_seed=3, **kw)
+    assert_same_ints(got, want)
+    return got
+
+
+@pytest.mark.parametrize("payload", [37, 100, 700, 4096, 0xFF00, 65536, [1, 36, 500, 65536]])
+def test_records_straddle_blocks(payload):
+    bam, bai = write_bam(REFS, _records(long_names=True), block_payload=payload)
+    _check(bam, bai)
+
+
+@pytest.mark.parametrize("level,strategy", [(0, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (9, zlib.Z_DEFAULT_STRATEGY),
+                                             (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE), (1, zlib.Z_FILTERED)])
+def test_deflate_block_kinds(level, strategy):
+    bam, bai = write_bam(REFS, _records(seed=2), level=level, strategy=strategy)
+    _check(bam, bai)
+
+
+def test_empty_blocks_extra_subfields_and_multi_member_streams():
+    def blocker(i, payload):
+        if i % 3 == 1:
+            # an empty block before the real one, and an unrelated gzip subfield ahead of BC
+            return bgzf_block(b"") + bgzf_block(payload, extra_subfield=True)
+        if i % 3 == 2:
+            # several deflate blocks inside one BGZF block (Z_FULL_FLUSH points), last one stored
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            third = len(payload) // 3
+            comp = co.compress(payload[:third]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(payload[third:2 * third]) + co.flush(zlib.Z_SYNC_FLUSH)
+            comp += co.compress(payload[2 * third:]) + co.flush()
+            bsize = 18 + len(comp) + 8 - 1
+            return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + comp +
+                    struct.pack("<II", zlib.crc32(payload) & 0xFFFFFFFF, len(payload)))
+        return None
+    bam, bai = write_bam(REFS, _records(seed=5), block_payload=3000, blocker=blocker)
+    _check(bam, bai)
+
+
+def test_no_eof_marker_and_chunked_submission():
+    bam, bai = write_bam(REFS, _records(seed=6), block_payload=2000, with_eof=False)
+    _check(bam, bai, chunk_bytes=5000)
+
+
+def test_header_only_file():
+    bam, bai = write_bam(REFS, [])
+    got = _check(bam, bai)
+    assert got["general"][0] == 0 and got["coverage"] == {} and got["quality"].shape[0] == 0
+
+
+def test_single_record_and_incompressible_payload():
+    rng = np.random.default_rng(0)
+    L = 30000
+    seq = "".join(rng.choice(list("ACGT"), size=L))
+    r = [rec(name="one", flag=0, ref=0, pos=10, cigar=f"{L}M", seq=seq, qual=rng.integers(0, 94, size=L).tolist(), aux=rng.bytes(5000))]
+    bam, bai = write_bam(REFS, r)
+    got = _check(bam, bai)
+    assert got["quality"].shape[0] == L
+
+
+def test_many_cigar_ops_and_wide_spans():
+    ops = "".join(f"{3 + (i % 5)}{'MID=XMNM'[i % 8]}" for i in range(3000))
+    ops = ops.replace("N", "M") + "2000N5M"
+    from bamutil import parse_cigar
+    cg = parse_cigar(ops)
+    qlen = sum(l for l, k in cg if k in (0, 1, 4, 7, 8))
+    r = [rec(name="cig", flag=0x41, ref=0, pos=100, cigar=ops, seq="A" * qlen, qual=[30] * qlen),
+         rec(name="cig2", flag=0x81, ref=0, pos=99000, cigar="50M5000N50M", seq="C" * 100, qual=[11] * 100)]  # overhangs chr1
+    bam, bai = write_bam(REFS, r)
+    got = _check(bam, bai)
+    assert got["nonsensical"] > 0
+
+
+def _engine_error(bam_bytes, **kw):
+    from ngs_b200 import ffi
+    with pytest.raises(ffi.NgsqError) as ei:
+        engine_ints(as_u8(bam_bytes), **kw)
+    return ei.value
+
+
+def test_corrupt_deflate_is_bad_block():
+    bam, bai = write_bam(REFS, _records(seed=7), block_payload=5000)
+    b = bytearray(bam)
+    first = len(bgzf_block(header_bytes(REFS)))
+    for k in range(first + 30, first + 60):
+        b[k] ^= 0xA5
+    e = _engine_error(bytes(b))
+    assert e.code in (-4, -5)  # invalid stream / ISIZE mismatch, or a CRC failure if it still inflates
+
+
+def test_crc_mismatch_is_reported():
+    bam, bai = write_bam(REFS, _records(seed=8), block_payload=5000)
+    b = bytearray(bam)
+    first = len(bgzf_block(header_bytes(REFS)))
+    total = struct.unpack_from("<H", b, first + 16)[0] + 1
+    b[first + total - 8] ^= 0xFF  # CRC32 field of the first record block
+    assert _engine_error(bytes(b)).code == -5
+    # with the check disabled (peak-throughput mode) the same file runs clean
+    engine_ints(as_u8(bytes(b)), crc=False)
+
+
+def test_isize_mismatch_is_bad_block():
+    bam, bai = write_bam(REFS, _records(seed=9), block_payload=5000)
+    b = bytearray(bam)
+    first = len(bgzf_block(header_bytes(REFS)))
+    total = struct.unpack_from("<H", b, first + 16)[0] + 1
+    isize = struct.unpack_from("<I", b, first + total - 4)[0]
+    struct.pack_into("<I", b, first + total - 4, isize - 1)
+    assert _engine_error(bytes(b), crc=False).code in (-4, -3, -6, -8)
+
+
+def test_quality_above_93_fails_the_run():
+    r = [rec(name="bad", flag=0, ref=0, pos=1, cigar="4M", seq="ACGT", qual=[10, 94, 10, 10])]
+    bam, bai = write_bam(REFS, r)
+    assert _engine_error(bam).code == -7
+
+
+def test_cigar_op_above_8_fails_the_run():
+    raw = bytearray(record(name="bad", flag=0, ref=0, pos=1, cigar="4M", seq="ACGT", qual=[10] * 4))
+    off = 4 + 32 + 4  # cigar word
+    struct.pack_into("<I", raw, off, (4 << 4) | 9)
+    bam, bai = write_bam(REFS, [(bytes(raw), dict(ref=0, pos=1, span=4, flag=0))])
+    assert _engine_error(bam).code == -6
+
+
+def test_mapped_pair_without_reference_ids_fails_like_the_reference_panics():
+    r = [rec(name="x", flag=0x41, ref=0, pos=1, cigar="4M", next_ref=-1, seq="ACGT")]
+    bam, bai = write_bam(REFS, r)
+    assert _engine_error(bam).code == -6
+
+
+def test_truncated_input():
+    from ngs_b200 import ffi
+    bam, bai = write_bam(REFS, _records(seed=10), block_payload=5000, with_eof=False)
+    e = _engine_error(bam[:-100])
+    assert e.code == -3
