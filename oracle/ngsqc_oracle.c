@@ -508,7 +508,10 @@ static int run(const uint8_t* bam, size_t bam_len, const uint8_t* bai, size_t ba
 }
 
 /* ------------------------------------------------------------------ JSON */
-static void jf(FILE* f, double v) { if (isnan(v) || isinf(v)) fputs("null", f); else fprintf(f, "%.17g", v); }
+static void jnum(FILE* f, const char* fmt, double v) { /* floats always carry a '.' or exponent so parsers keep them floats */
+  char b[64]; snprintf(b, sizeof b, fmt, v); fputs(b, f); if (!strpbrk(b, ".eE")) fputs(".0", f);
+}
+static void jf(FILE* f, double v) { if (isnan(v) || isinf(v)) fputs("null", f); else jnum(f, "%.17g", v); }
 static void jhist(FILE* f, const uint64_t* v, uint64_t cap) {
   fputs("{\"values\":[", f);
   for (uint64_t i = 0; i <= cap; ++i) fprintf(f, "%s%llu", i ? "," : "", (unsigned long long)v[i]);
@@ -574,7 +577,7 @@ static int write_json(const results_t* R, FILE* f) {
       for (uint32_t c = 0; c < R->n_ref; ++c) if (R->touched[c]) { fprintf(f, "%s\"%s\":%llu", first ? "" : ",", R->refs[c].name, (unsigned long long)R->cov_ignored[c]); first = 0; } }
     fputs("}},\"coverage_distribution\":", f); jhist(f, R->cov_dist.v, COV_HIST);
     fputs(",\"genome_covered_by\":{", f);
-    for (int k = 0; k < 6; ++k) { fprintf(f, "%s\"%dx\":", k ? "," : "", 10 * (k + 1)); if (isnan(R->covered_by[k]) || isinf(R->covered_by[k])) fputs("null", f); else fprintf(f, "%.9g", (double)R->covered_by[k]); }
+    for (int k = 0; k < 6; ++k) { fprintf(f, "%s\"%dx\":", k ? "," : "", 10 * (k + 1)); if (isnan(R->covered_by[k]) || isinf(R->covered_by[k])) fputs("null", f); else jnum(f, "%.9g", (double)R->covered_by[k]); }
     fputs("}},", f);
   } else fputs("\"coverage\":null,", f);
   fputs("\"edits\":null}\n", f);

@@ -60,8 +60,8 @@ def test_deflate_block_kinds(level, strategy):
 def test_empty_blocks_extra_subfields_and_multi_member_streams():
     def blocker(i, payload):
         if i % 3 == 1:
-            # an empty block before the real one, and an unrelated gzip subfield ahead of BC
-            return bgzf_block(b"") + bgzf_block(payload, extra_subfield=True)
+            # an unrelated gzip subfield ahead of BC, and an empty block after the real one
+            return bgzf_block(payload, extra_subfield=True) + bgzf_block(b"")
         if i % 3 == 2:
             # several deflate blocks inside one BGZF block (Z_FULL_FLUSH points), last one stored
             co = zlib.compressobj(6, zlib.DEFLATED, -15)
@@ -103,8 +103,8 @@ def test_many_cigar_ops_and_wide_spans():
     from bamutil import parse_cigar
     cg = parse_cigar(ops)
     qlen = sum(l for l, k in cg if k in (0, 1, 4, 7, 8))
-    r = [rec(name="cig", flag=0x41, ref=0, pos=100, cigar=ops, seq="A" * qlen, qual=[30] * qlen),
-         rec(name="cig2", flag=0x81, ref=0, pos=99000, cigar="50M5000N50M", seq="C" * 100, qual=[11] * 100)]  # overhangs chr1
+    r = [rec(name="cig", flag=0x40, ref=0, pos=100, cigar=ops, seq="A" * qlen, qual=[30] * qlen),
+         rec(name="cig2", flag=0x80, ref=0, pos=99000, cigar="50M5000N50M", seq="C" * 100, qual=[11] * 100)]  # overhangs chr1
     bam, bai = write_bam(REFS, r)
     got = _check(bam, bai)
     assert got["nonsensical"] > 0
