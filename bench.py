@@ -331,7 +331,7 @@ def main():
             "config": {"workload": ("configs[1]: 100M-record 2x150bp WGS-shaped synthetic BAM, all facets incl. coverage" if N == 1 and per_gpu == 100_000_000
                                     else f"{int(all_rec)}-record 2x150bp WGS-shaped synthetic BAM partitioned by contig ranges over {N} GPU(s), all facets incl. coverage"),
                        "records": int(all_rec), "compressed_bytes": int(all_C), "inflated_bytes": int(all_D), "zlib_level": level,
-                       "crc_check": not args.no_crc, "inflate_lanes": args.lanes or 8,
+                       "crc_check": not args.no_crc, "inflate_lanes": args.lanes or 16,
                        "l2": "inputs (GBs) far exceed the 126 MB L2; no flush needed", "generation_s": gen_s,
                        "stage_ms": {k: stats[k] for k in ["ms_inflate", "ms_crc", "ms_scan", "ms_facets", "ms_coverage"]}},
             "roofline": {"bound": "hbm", "kernel": "inflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

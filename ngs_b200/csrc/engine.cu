@@ -200,9 +200,9 @@ int launch_inflate_g(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_
 int launch_inflate(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_t* out, uint32_t* queue, uint32_t* status, cudaStream_t s) {
   switch (e->cfg.inflate_lanes) {
     case 4: return launch_inflate_g<4>(e, blocks, n, out, queue, status, s);
-    case 16: return launch_inflate_g<16>(e, blocks, n, out, queue, status, s);
+    case 8: return launch_inflate_g<8>(e, blocks, n, out, queue, status, s);
     case 32: return launch_inflate_g<32>(e, blocks, n, out, queue, status, s);
-    default: return launch_inflate_g<8>(e, blocks, n, out, queue, status, s);
+    default: return launch_inflate_g<16>(e, blocks, n, out, queue, status, s);
   }
 }
 
@@ -338,7 +338,7 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   ne->device = device;
   if (cfg) memcpy(&ne->cfg, cfg, std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(ngsq_config), sizeof(ngsq_config)));
   if (!ne->cfg.flags) ne->cfg.flags = NGSQ_F_RECORD_FACETS | NGSQ_F_COVERAGE;
-  if (ne->cfg.inflate_lanes != 4 && ne->cfg.inflate_lanes != 16 && ne->cfg.inflate_lanes != 32) ne->cfg.inflate_lanes = 8;
+  if (ne->cfg.inflate_lanes != 4 && ne->cfg.inflate_lanes != 8 && ne->cfg.inflate_lanes != 32) ne->cfg.inflate_lanes = 16;  // measured best on B200 (profiles/)
   e = ne;
   auto bail = [&](int code) { std::string m = e->err; ngsq_destroy(e); g_create_err = m; return code; };
 #define CUC(call) do { cudaError_t _r = (call); if (_r != cudaSuccess) { fail(e, NGSQ_E_CUDA, "%s: %s", #call, cudaGetErrorString(_r)); return bail(NGSQ_E_CUDA); } } while (0)
