@@ -21,6 +21,7 @@
 #include "crc32.cuh"
 #include "facets.cuh"
 #include "inflate.cuh"
+#include "inflate2.cuh"
 #include "recscan.cuh"
 
 using namespace ngsq;
@@ -120,6 +121,8 @@ struct ngsq_engine {
   std::vector<uint32_t> h_crc;
   uint64_t comp_bytes_total = 0;
   uint32_t* d_status = nullptr;
+  uint32_t* d_bitmap = nullptr;  // v2 inflate: one bit per inflated byte, kBitmapWords per block
+  size_t bitmap_cap = 0;         // blocks
   uint32_t* d_queue = nullptr;
   uint32_t n_launches = 0;
   static constexpr uint32_t kQueueSlots = 4096;
@@ -193,6 +196,26 @@ int launch_inflate_g(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_
   uint32_t grid = std::min<uint32_t>(want, (uint32_t)(e->n_sm * occ));
   if (grid == 0) return NGSQ_OK;
   inflate_kernel<G><<<grid, kInflateThreads, smem, s>>>(out, blocks, n, queue, status);
+  CU(cudaGetLastError());
+  return NGSQ_OK;
+}
+
+// v2: lane-per-block Huffman decode, then warp-per-block LZ77 resolve (inflate2.cuh)
+int launch_inflate_v2(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_t* out, uint32_t* queue, uint32_t* status,
+                      uint32_t* bitmap, cudaStream_t s) {
+  if (!n) return NGSQ_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(inflate_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem));
+    attr_set = true;
+  }
+  CU(cudaMemsetAsync(bitmap, 0, (size_t)n * kBitmapWords * 4, s));
+  const uint32_t per_cta = kDecThreads;
+  uint32_t grid = std::min<uint32_t>((n + per_cta - 1) / per_cta, (uint32_t)e->n_sm);
+  inflate_decode_kernel<<<grid, kDecThreads, kDecSmem, s>>>(out, blocks, n, queue, status, bitmap);
+  CU(cudaGetLastError());
+  uint32_t rgrid = std::min<uint32_t>((n + kResWarps - 1) / kResWarps, (uint32_t)e->n_sm * 8);
+  inflate_resolve_kernel<<<rgrid, kResThreads, 0, s>>>(out, blocks, n, bitmap, status);
   CU(cudaGetLastError());
   return NGSQ_OK;
 }
@@ -309,7 +332,24 @@ int inflate_new_blocks(ngsq_engine* e, uint32_t first_new, uint32_t n_new) {
   CU(cudaEventCreate(&a));
   CU(cudaEventCreate(&b));
   CU(cudaEventRecord(a, e->s_comp));
-  int rc = launch_inflate(e, e->d_blocks + first_new, n_new, e->d_out, e->d_queue + e->n_launches, e->d_status + first_new, e->s_comp);
+  int rc;
+  if (e->cfg.inflate_lanes == 1) {
+    if (total > e->bitmap_cap) {
+      // earlier submits' bitmaps are dead once their resolve kernels ran: no need to keep them
+      CU(cudaStreamSynchronize(e->s_comp));
+      if (e->d_bitmap) cudaFree(e->d_bitmap);
+      e->d_bitmap = nullptr;
+      size_t cap = std::max<size_t>(total, e->blocks_cap);
+      cudaError_t r2 = cudaMalloc(&e->d_bitmap, cap * kBitmapWords * 4);
+      if (r2 != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc match bitmap (%zu bytes): %s", cap * kBitmapWords * 4, cudaGetErrorString(r2));
+      e->bitmap_cap = cap;
+    }
+    rc = launch_inflate_v2(e, e->d_blocks + first_new, n_new, e->d_out, e->d_queue + e->n_launches, e->d_status + first_new,
+                           e->d_bitmap + (size_t)first_new * kBitmapWords, e->s_comp);
+    e->other_launches += 1;  // resolve kernel (the decode kernel is counted as the inflate launch)
+  } else {
+    rc = launch_inflate(e, e->d_blocks + first_new, n_new, e->d_out, e->d_queue + e->n_launches, e->d_status + first_new, e->s_comp);
+  }
   if (rc) return rc;
   CU(cudaEventRecord(b, e->s_comp));
   e->inflate_events.push_back({a, b});
@@ -338,7 +378,8 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   ne->device = device;
   if (cfg) memcpy(&ne->cfg, cfg, std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(ngsq_config), sizeof(ngsq_config)));
   if (!ne->cfg.flags) ne->cfg.flags = NGSQ_F_RECORD_FACETS | NGSQ_F_COVERAGE;
-  if (ne->cfg.inflate_lanes != 4 && ne->cfg.inflate_lanes != 8 && ne->cfg.inflate_lanes != 32) ne->cfg.inflate_lanes = 16;  // measured best on B200 (profiles/)
+  // 0 / 1 = v2 (lane-per-block decode + warp-per-block resolve); 4/8/16/32 = v1 group-per-block kernel (kept for A/B runs)
+  if (ne->cfg.inflate_lanes != 4 && ne->cfg.inflate_lanes != 8 && ne->cfg.inflate_lanes != 16 && ne->cfg.inflate_lanes != 32) ne->cfg.inflate_lanes = 1;
   e = ne;
   auto bail = [&](int code) { std::string m = e->err; ngsq_destroy(e); g_create_err = m; return code; };
 #define CUC(call) do { cudaError_t _r = (call); if (_r != cudaSuccess) { fail(e, NGSQ_E_CUDA, "%s: %s", #call, cudaGetErrorString(_r)); return bail(NGSQ_E_CUDA); } } while (0)
@@ -387,7 +428,7 @@ void ngsq_destroy(ngsq_engine* e) {
   for (auto& p : e->inflate_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_c, e->ev_d, e->ev_e, e->ev_f}) if (ev) cudaEventDestroy(ev);
   void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_res, e->d_out,
-                  e->d_blocks, e->d_status, e->d_queue, e->d_out_off, e->d_coff, e->d_base, e->d_rec, e->d_first, e->d_landed,
+                  e->d_blocks, e->d_status, e->d_bitmap, e->d_queue, e->d_out_off, e->d_coff, e->d_base, e->d_rec, e->d_first, e->d_landed,
                   e->d_count, e->d_crc, e->d_flags, e->d_crc_tables};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& sg : e->comp_segs) cudaFree(sg.ptr);
@@ -943,7 +984,13 @@ int ngsq_inflate_to_host(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uin
     CU(cudaMemsetAsync(d_st, 0, hb.size() * 4 + 4, s));
     CU(cudaMemcpyAsync(d_in, bgzf, used, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_b, hb.data(), hb.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, s));
-    ret = launch_inflate(e, d_b, (uint32_t)hb.size(), d_o, d_q, d_st, s);
+    uint32_t* d_bm = nullptr;
+    if (e->cfg.inflate_lanes == 1) {
+      CU(cudaMalloc(&d_bm, hb.size() * kBitmapWords * 4));
+      ret = launch_inflate_v2(e, d_b, (uint32_t)hb.size(), d_o, d_q, d_st, d_bm, s);
+    } else {
+      ret = launch_inflate(e, d_b, (uint32_t)hb.size(), d_o, d_q, d_st, s);
+    }
     std::vector<uint32_t> st(hb.size());
     if (!ret) {
       CU(cudaMemcpyAsync(out, d_o, total, cudaMemcpyDeviceToHost, s));
@@ -952,7 +999,9 @@ int ngsq_inflate_to_host(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uin
       for (size_t i = 0; i < st.size(); ++i)
         if (st[i]) { ret = fail(e, NGSQ_E_BAD_BLOCK, "block %zu failed to inflate (status %u)", i, st[i]); break; }
     }
+    cudaStreamSynchronize(s);
     cudaFree(d_o); cudaFree(d_b); cudaFree(d_st);
+    if (d_bm) cudaFree(d_bm);
   }
   cudaFree(d_in);
   return ret;

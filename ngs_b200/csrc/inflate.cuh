@@ -19,16 +19,9 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "inflate_lane.cuh"  // BlockDesc, kBlk* status codes
+
 namespace ngsq {
-
-struct BlockDesc {
-  uint64_t in_off;   // absolute device address of the DEFLATE payload
-  uint64_t out_off;  // offset of this block's first inflated byte
-  uint32_t clen;     // DEFLATE payload length
-  uint32_t isize;    // expected inflated size
-};
-
-enum : uint32_t { kBlkOk = 0, kBlkBadStream = 1, kBlkIsize = 2, kBlkOverrun = 3 };
 
 constexpr int kLLBits = 10;
 constexpr int kDBits = 8;

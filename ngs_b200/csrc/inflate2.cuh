@@ -1,0 +1,159 @@
+// K2 (v2) — BGZF inflate as two kernels (reference: the inflate noodles-bgzf/miniz_oxide perform
+// under bam::Reader, src/utils/formats/bam.rs:41-44, src/qc/command.rs:305 and :350).
+//
+//   inflate_decode_kernel   one BGZF block per LANE: 32 independent Huffman decoders per warp
+//                           instruction (inflate_lane.cuh).  Literals go to their final place,
+//                           matches leave a 3-byte token in place + a bit in the block's bitmap.
+//                           Persistent grid, one CTA per SM (shared-memory bound: one table slab
+//                           per lane); a warp pulls 32 consecutive blocks at a time so that the
+//                           lanes of a warp meet their DEFLATE block headers together (zlib ends a
+//                           block every 16383 symbols) and parse/build them in lock step.
+//   inflate_resolve_kernel  one BGZF block per WARP: walks the bitmap in stream order, 32 tokens
+//                           per step, one lane per LZ77 match; a match waits while its source
+//                           still overlaps an unresolved earlier match.
+// Both are issue/L1-bound integer kernels; HBM traffic is C + D (+ D/8 bitmap) per pass.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "inflate_lane.cuh"
+
+namespace ngsq {
+
+constexpr int kDecBatch = 32;  // symbols per lane between header / overrun checks
+constexpr int kDecWarps = (227 * 1024 / kSlabBytes) / 32 > 16 ? 16 : (227 * 1024 / kSlabBytes) / 32;
+constexpr int kDecThreads = kDecWarps * 32;
+constexpr size_t kDecSmem = (size_t)kDecThreads * kSlabBytes;
+
+__global__ void __launch_bounds__(kDecThreads, 1)
+inflate_decode_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, uint32_t n_blocks,
+                      uint32_t* __restrict__ queue, uint32_t* __restrict__ status, uint32_t* __restrict__ bitmap) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t lane = threadIdx.x & 31;
+  Lane L;
+  L.slab = smem_raw + (size_t)threadIdx.x * kSlabBytes;
+  L.state = LS_IDLE;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(queue, 32u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n_blocks) break;
+    const uint32_t b = base + lane;
+    if (b < n_blocks) L.begin_block(blocks[b], out, bitmap + (size_t)b * kBitmapWords);
+    else L.state = LS_IDLE;
+    while (__any_sync(0xFFFFFFFFu, L.state != LS_IDLE)) {
+      if (L.state == LS_HEADER) L.header();
+      __syncwarp();
+#pragma unroll 1
+      for (int it = 0; it < kDecBatch; ++it) {
+        if (L.state == LS_DECODE) L.step();
+        if (!__any_sync(0xFFFFFFFFu, L.state == LS_DECODE)) break;
+      }
+      if (L.state == LS_DECODE && L.overran()) L.end_block(kBlkBadStream);
+    }
+    if (b < n_blocks && L.err) status[b] = L.err;
+  }
+}
+
+constexpr int kResThreads = 256;
+constexpr int kResWarps = kResThreads / 32;
+constexpr int kResList = 352;  // matches that can start inside 1024 bytes (every match is >= 3 bytes)
+
+// the 8 bytes at s (any alignment) through three aligned 32-bit loads and two funnel shifts: one
+// L1 wavefront per lane per load instead of one per byte (the resolve kernel is L1-wavefront bound)
+__device__ __forceinline__ uint2 load8_unaligned(const uint8_t* s) {
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(s) & ~uintptr_t(3));
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
+  const uint32_t w0 = a[0], w1 = a[1], w2 = a[2];
+  return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+
+__device__ __forceinline__ void store_bytes(uint8_t* d, uint2 v, uint32_t n) {  // n in 1..8
+  d[0] = (uint8_t)v.x;
+  if (n > 1) d[1] = (uint8_t)(v.x >> 8);
+  if (n > 2) d[2] = (uint8_t)(v.x >> 16);
+  if (n > 3) d[3] = (uint8_t)(v.x >> 24);
+  if (n > 4) d[4] = (uint8_t)v.y;
+  if (n > 5) d[5] = (uint8_t)(v.y >> 8);
+  if (n > 6) d[6] = (uint8_t)(v.y >> 16);
+  if (n > 7) d[7] = (uint8_t)(v.y >> 24);
+}
+
+// one lane copies one match; the source never includes bytes of the match itself (periodic extension)
+__device__ __forceinline__ void resolve_copy(uint8_t* dst, uint32_t mlen, uint32_t dist) {
+  const uint8_t* src = dst - dist;
+  if (dist >= 8 || dist >= mlen) {
+    // 8 bytes per step: a step reads only final bytes or bytes this lane wrote in earlier steps
+    for (uint32_t k = 0; k < mlen; k += 8) store_bytes(dst + k, load8_unaligned(src + k), min(8u, mlen - k));
+  } else {
+    // overlapping run with a period below 8: replicate the period from registers
+    const uint2 pat = load8_unaligned(src);
+    const uint64_t P = (uint64_t)pat.x | ((uint64_t)pat.y << 32);
+    uint32_t ph = 0;
+    for (uint32_t k = 0; k < mlen; ++k) {
+      dst[k] = (uint8_t)(P >> (8 * ph));
+      ph = ph + 1 == dist ? 0 : ph + 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kResThreads)
+inflate_resolve_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, uint32_t n_blocks,
+                       const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ status) {
+  __shared__ uint16_t s_pos[kResWarps][kResList];
+  const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const uint32_t n_warps = gridDim.x * kResWarps;
+  uint16_t* list = s_pos[wic];
+  for (uint32_t b = blockIdx.x * kResWarps + wic; b < n_blocks; b += n_warps) {
+    if (status[b]) continue;  // failed blocks carry no trustworthy tokens
+    const BlockDesc d = blocks[b];
+    uint8_t* ob = out + d.out_off;
+    const uint32_t* bmp = bitmap + (size_t)b * kBitmapWords;
+    const uint32_t n_sw = (d.isize + 1023) >> 10;
+    for (uint32_t sw = 0; sw < n_sw; ++sw) {
+      uint32_t word = bmp[sw * 32 + lane];
+      const uint32_t cnt = __popc(word);
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((int)lane >= o) incl += t;
+      }
+      const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      if (!total) continue;
+      uint32_t o = incl - cnt;
+      const uint32_t pbase = (sw << 10) + (lane << 5);
+      while (word) {
+        const uint32_t bit = __ffs(word) - 1;
+        word &= word - 1;
+        list[o++] = (uint16_t)(pbase + bit);
+      }
+      __syncwarp();
+      for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t j = base + lane;
+        const bool active = j < total;
+        uint32_t pos = 0, mlen = 0, dist = 1;
+        if (active) {
+          pos = list[j];
+          const uint8_t* t = ob + pos;
+          const uint32_t tok = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16);
+          mlen = (tok & 255u) + 3u;
+          dist = (tok >> 8) + 1u;
+        }
+        const uint32_t src_end = pos - dist + min(mlen, dist);
+        uint32_t done = __ballot_sync(0xFFFFFFFFu, !active);
+        while (done != 0xFFFFFFFFu) {
+          const int f = __ffs(~done) - 1;
+          const uint32_t fpos = __shfl_sync(0xFFFFFFFFu, pos, f);
+          const bool ready = !((done >> lane) & 1u) && ((int)lane == f || src_end <= fpos);
+          if (ready) resolve_copy(ob + pos, mlen, dist);
+          __syncwarp();
+          done |= __ballot_sync(0xFFFFFFFFu, ready);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+}  // namespace ngsq

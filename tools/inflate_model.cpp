@@ -1,0 +1,139 @@
+// CPU model of the v2 inflate kernels (test tooling; NOT part of the product library).
+// Compiles ngs_b200/csrc/inflate_lane.cuh for the host, runs the per-lane decoder plus a scalar
+// restatement of the resolve pass over every BGZF block of a file, checks the bytes against zlib
+// and prints symbol statistics that drive kernel design decisions.
+//   g++ -O2 -std=c++17 -DNGSQ_HOST_MODEL -o /tmp/inflate_model tools/inflate_model.cpp -lz
+//   /tmp/inflate_model file.bam [max_blocks]
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../ngs_b200/csrc/inflate_lane.cuh"
+
+using namespace ngsq;
+
+int main(int argc, char** argv) {
+  if (argc < 2) { fprintf(stderr, "usage: %s file.bam [max_blocks]\n", argv[0]); return 2; }
+  FILE* f = fopen(argv[1], "rb");
+  if (!f) { perror("open"); return 2; }
+  fseek(f, 0, SEEK_END);
+  size_t n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<uint8_t> buf(n + 1024, 0);
+  if (fread(buf.data(), 1, n, f) != n) { perror("read"); return 2; }
+  fclose(f);
+  size_t max_blocks = argc > 2 ? strtoull(argv[2], nullptr, 10) : ~size_t(0);
+
+  InflateCounters ctr;
+  std::vector<uint8_t> slab(kSlabBytes);
+
+  std::vector<uint32_t> bitmap(kBitmapWords);
+  std::vector<uint8_t> out(65536 + 64), ref(65536);
+  uint64_t hist_len[260] = {0}, n_blocks = 0, total_out = 0, total_in = 0, bad = 0, resolve_tokens = 0;
+  uint64_t dist_small = 0, dist_lt_len = 0;
+  size_t o = 0;
+  while (o + 18 <= n && n_blocks < max_blocks) {
+    const uint8_t* h = &buf[o];
+    if (h[0] != 0x1f || h[1] != 0x8b) { fprintf(stderr, "bad magic at %zu\n", o); return 1; }
+    uint32_t xlen = h[10] | (h[11] << 8);
+    uint32_t bsize = h[16] | (h[17] << 8);
+    size_t total = (size_t)bsize + 1;
+    uint32_t isize;
+    memcpy(&isize, h + total - 4, 4);
+    uint32_t crc;
+    memcpy(&crc, h + total - 8, 4);
+    uint32_t hdr = 12 + xlen;
+    uint32_t clen = (uint32_t)total - hdr - 8;
+    if (isize) {
+      for (int mis = 0; mis < 4; mis += 3) {  // two output alignments
+        BlockDesc d;
+        d.in_off = (uint64_t)(uintptr_t)(h + hdr);
+        d.out_off = 16 + mis * 3;
+        d.clen = clen;
+        d.isize = isize;
+        memset(out.data(), 0xAA, out.size());
+        memset(bitmap.data(), 0, kBitmapWords * 4);
+        Lane L;
+        L.slab = slab.data();
+
+        L.ctr = mis == 0 ? &ctr : nullptr;
+        L.begin_block(d, out.data(), bitmap.data());
+        while (L.state != LS_IDLE) {
+          if (L.state == LS_HEADER) L.header();
+          else {
+            L.step();
+            if (L.state == LS_DECODE && L.overran()) L.end_block(kBlkBadStream);
+          }
+        }
+        if (L.err) { fprintf(stderr, "block at %zu: err %u\n", o, L.err); bad++; break; }
+        // guard bytes
+        uint8_t* ob = out.data() + d.out_off;
+        for (int g = 1; g <= 4; ++g)
+          if (ob[-g] != 0xAA || ob[isize + g - 1] != 0xAA) { fprintf(stderr, "block at %zu: wrote outside (mis %d)\n", o, mis); bad++; }
+        // resolve pass (scalar, stream order)
+        for (uint32_t w = 0; w < kBitmapWords; ++w) {
+          uint32_t m = bitmap[w];
+          while (m) {
+            uint32_t bit = __builtin_ctz(m);
+            m &= m - 1;
+            uint32_t p = w * 32 + bit;
+            uint32_t tok = ob[p] | (ob[p + 1] << 8) | (ob[p + 2] << 16);
+            uint32_t mlen = (tok & 255) + 3, dist = (tok >> 8) + 1;
+            if (mis == 0) { hist_len[mlen]++; resolve_tokens++; dist_small += dist < 4; dist_lt_len += dist < mlen; }
+            for (uint32_t k = 0; k < mlen; ++k) ob[p + k] = ob[p + k - dist];
+          }
+        }
+        // zlib
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        inflateInit2(&zs, -15);
+        zs.next_in = const_cast<uint8_t*>(h + hdr);
+        zs.avail_in = clen;
+        zs.next_out = ref.data();
+        zs.avail_out = 65536;
+        int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        if (rc != Z_STREAM_END || zs.total_out != isize) { fprintf(stderr, "zlib failed at %zu\n", o); return 1; }
+        if (memcmp(ref.data(), ob, isize) != 0) {
+          uint32_t k = 0;
+          while (ref[k] == ob[k]) ++k;
+          fprintf(stderr, "block at %zu (mis %d): MISMATCH at byte %u of %u\n", o, mis, k, isize);
+          bad++;
+        }
+        if (crc32(0, ref.data(), isize) != crc) { fprintf(stderr, "crc mismatch at %zu\n", o); bad++; }
+      }
+      n_blocks++;
+      total_out += isize;
+      total_in += clen;
+    }
+    o += total;
+  }
+  printf("blocks %llu, in %llu, out %llu (ratio %.2f), bad %llu\n", (unsigned long long)n_blocks, (unsigned long long)total_in,
+         (unsigned long long)total_out, (double)total_out / total_in, (unsigned long long)bad);
+  printf("symbols %llu (%.3f per out byte): literals %llu (%.1f%%), matches %llu (%.1f%%), avg match len %.2f, match bytes %.1f%% of output\n",
+         (unsigned long long)ctr.symbols, (double)ctr.symbols / total_out, (unsigned long long)ctr.literals, 100.0 * ctr.literals / ctr.symbols,
+         (unsigned long long)ctr.matches, 100.0 * ctr.matches / ctr.symbols, (double)ctr.match_bytes / (ctr.matches ? ctr.matches : 1),
+         100.0 * ctr.match_bytes / total_out);
+  printf("bits per symbol %.2f\n", 8.0 * total_in / ctr.symbols);
+  printf("ll code length %%:");
+  for (int l = 1; l <= 15; ++l) printf(" %d:%.1f", l, 100.0 * ctr.ll_len_hist[l] / ctr.symbols);
+  printf("\ndist code length %%:");
+  for (int l = 1; l <= 15; ++l) printf(" %d:%.1f", l, 100.0 * ctr.d_len_hist[l] / (ctr.matches ? ctr.matches : 1));
+  printf("\n");
+  printf("deflate blocks per BGZF block %.2f (stored %llu, fixed %llu); symbols per deflate block %.0f\n", (double)ctr.headers / n_blocks,
+         (unsigned long long)ctr.stored, (unsigned long long)ctr.fixed, (double)ctr.symbols / ctr.headers);
+  printf("stores: %llu chunk + %llu edge = %.3f per output byte\n", (unsigned long long)ctr.chunk_stores, (unsigned long long)ctr.edge_stores,
+         (double)(ctr.chunk_stores + ctr.edge_stores) / total_out);
+  printf("dist<4: %.1f%% of matches, dist<len: %.1f%%\n", 100.0 * dist_small / (resolve_tokens ? resolve_tokens : 1), 100.0 * dist_lt_len / (resolve_tokens ? resolve_tokens : 1));
+  printf("match length histogram (cumulative %%):");
+  uint64_t cum = 0;
+  for (int l = 3; l <= 258; ++l) {
+    cum += hist_len[l];
+    if (l <= 12 || l == 16 || l == 24 || l == 32 || l == 64 || l == 128 || l == 258) printf(" <=%d:%.1f", l, 100.0 * cum / (resolve_tokens ? resolve_tokens : 1));
+  }
+  printf("\n");
+  return bad ? 1 : 0;
+}

@@ -26,8 +26,17 @@ for ln in dis:
         lines.append((cur, m.group(2).strip()))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr = rows[1]
-body = rows[2:]
+# the page holds one section per profiled launch: "Kernel Name",<name> / header row / one row per SASS instruction
+sections, cur_sec = [], None
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        cur_sec = {"name": r[1], "rows": []}
+        sections.append(cur_sec)
+    elif cur_sec is not None:
+        cur_sec["rows"].append(r)
+sec = [x for x in sections if sym in x["name"]][0]
+hdr = sec["rows"][0]
+body = sec["rows"][1:]
 ie, ss, at = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Avg. Threads Executed")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 assert len(body) == len(lines), (len(body), len(lines))
