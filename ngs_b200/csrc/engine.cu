@@ -742,12 +742,12 @@ int ngsq_finish(ngsq_engine* e) {
     P.res = e->d_res; P.qual = e->d_res + e->qual_off;
     P.qpos_smem = std::min<uint32_t>(std::max<uint32_t>(max_lseq, 1), 256);
     P.qpos_cap = e->qpos_cap;
-    size_t smem = ((size_t)P.qpos_smem * 94 + kTlenPad + kGcPad + kCigWords) * 4;
+    size_t smem = ((size_t)P.qpos_smem * kQualStride + kTlenPad + kGcPad + kCigWords) * 4;
     CU(cudaFuncSetAttribute(facets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, facets_kernel, kFacetThreads, smem));
     if (occ < 1) occ = 1;
-    uint64_t want = (n_rec + (kFacetThreads / 32) - 1) / (kFacetThreads / 32);
+    uint64_t want = (n_rec + kFacetThreads - 1) / kFacetThreads;  // a warp takes 32 records per step
     uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)e->n_sm * occ);
     facets_kernel<<<grid, kFacetThreads, smem, s>>>(P);
     CU(cudaGetLastError());

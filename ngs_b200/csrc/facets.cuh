@@ -4,9 +4,9 @@
 //   general.rs:31-124, template_length.rs:79-87, gc_content.rs:38-100,
 //   quality_scores.rs:37-49, coverage.rs:148-180 (+ the query filter of command.rs:369-377).
 //
-// One warp per record (grid-stride).  Flag-derived counters are uniform across the warp, so
-// every lane owns one counter in a register (lane k adds bit k of the record's counter mask):
-// no atomics at all for General / record tallies.  Histograms (tlen, gc, per-position quality,
+// Two phases per 32 records (see facets_kernel): header-derived facets with one record per lane,
+// per-base facets with one record per warp step.  Flag-derived counters: lane k owns counter k
+// and adds the popcount of a ballot of bit k: no atomics for General / record tallies.  Histograms (tlen, gc, per-position quality,
 // CIGAR kinds) are privatised in shared memory per CTA and flushed once with 64-bit global
 // reductions.  Quality positions beyond the shared-memory table (long reads) go straight to
 // the L2-resident global table.  Coverage is two signed global reductions per record into the
@@ -37,7 +37,7 @@ constexpr uint32_t R_FIXED_WORDS = 1184;
 // per contig slot: [0] touched, [1] pileup_too_large, [2..2051) depth histogram, [2051..) bin sums
 constexpr uint32_t COV_TOUCHED = 0, COV_TOO_LARGE = 1, COV_HIST = 2, COV_BINS = 2051;
 
-constexpr int kFacetThreads = 256;
+constexpr int kFacetThreads = 512;
 constexpr uint32_t kTlenPad = 1028, kGcPad = 104, kCigWords = 18 * 32;
 
 struct FacetParams {
@@ -69,13 +69,24 @@ __device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
   return x ^ (x >> 31);
 }
 
+// Work split (ncu, profiles/: the warp-per-record form spent ~300 warp instructions per record, most
+// of them on header fields with one useful lane):
+//   phase A  lane <-> record: 32 records per warp step.  Header fields, validation, CIGAR (short
+//            CIGARs per lane; long ones — long reads — cooperatively), coverage scatter, General
+//            flag bits, template length, GC eligibility + window offset.
+//   phase B  warp <-> record, 32 times: the per-base work (GC window, quality-by-position), all
+//            lanes on consecutive bytes of one record.
+// General / record counters are summed with one ballot + popcount per counter per 32 records.
+constexpr uint32_t kQualStride = 95;   // 94 scores + 1: odd stride, lanes on consecutive positions hit distinct banks
+constexpr uint32_t kShortCigar = 8;    // CIGARs up to this many ops are tallied by the record's own lane
+
 __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
   extern __shared__ uint32_t sm[];
   uint32_t* s_qual = sm;
-  uint32_t* s_tlen = s_qual + P.qpos_smem * 94;
+  uint32_t* s_tlen = s_qual + P.qpos_smem * kQualStride;
   uint32_t* s_gc = s_tlen + kTlenPad;
   uint32_t* s_cig = s_gc + kGcPad;
-  const uint32_t n_sm = P.qpos_smem * 94 + kTlenPad + kGcPad + kCigWords;
+  const uint32_t n_sm = P.qpos_smem * kQualStride + kTlenPad + kGcPad + kCigWords;
   for (uint32_t i = threadIdx.x; i < n_sm; i += blockDim.x) sm[i] = 0;
   __syncthreads();
 
@@ -83,47 +94,78 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
   const uint32_t warps_per_cta = blockDim.x >> 5;
   const uint64_t n_warps = (uint64_t)gridDim.x * warps_per_cta;
   const bool do_rec = P.flags & 1u, do_cov = P.flags & 2u;
-  uint32_t acc = 0;          // lane-owned counter (see mask bits below)
+  uint32_t acc = 0;                        // lane k owns counter k (bit k of every record's `bits`)
+  uint32_t sum_gc = 0, sum_at = 0, sum_oth = 0;  // warp-uniform
   uint32_t err_qual = 0, err_rec = 0, max_qpos = 0;
 
-  for (uint64_t r = (uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); r < P.n_rec; r += n_warps) {
-    const uint64_t rv = P.rec[r];
-    const uint32_t b = (uint32_t)(rv >> 16), uoff = (uint32_t)(rv & 0xFFFF);
-    const uint8_t* p = P.d + P.out_off[b] + uoff;
-    uint32_t hw = lane < 9 ? ld_u32_unaligned(p + 4 * lane) : 0;
-    const uint32_t bs = __shfl_sync(0xFFFFFFFFu, hw, 0);
-    const int32_t ref = (int32_t)__shfl_sync(0xFFFFFFFFu, hw, 1);
-    const int32_t pos = (int32_t)__shfl_sync(0xFFFFFFFFu, hw, 2);
-    const uint32_t w3 = __shfl_sync(0xFFFFFFFFu, hw, 3);
-    const uint32_t w4 = __shfl_sync(0xFFFFFFFFu, hw, 4);
-    const uint32_t lseq = __shfl_sync(0xFFFFFFFFu, hw, 5);
-    const int32_t nref = (int32_t)__shfl_sync(0xFFFFFFFFu, hw, 6);
-    const int32_t tlen = (int32_t)__shfl_sync(0xFFFFFFFFu, hw, 8);
-    const uint32_t lname = w3 & 255, mapq = (w3 >> 8) & 255, ncig = w4 & 0xFFFF, f = w4 >> 16;
-    const uint64_t need = 32ull + lname + 4ull * ncig + (lseq + 1ull) / 2 + lseq;
-    if (need > bs || ref < -1 || ref >= P.n_ref || nref < -1 || nref >= P.n_ref) { err_rec = 1; continue; }
+  for (uint64_t r0 = ((uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5)) * 32; r0 < P.n_rec; r0 += n_warps * 32) {
+    // ================= phase A: one record per lane =================
+    const uint64_t r = r0 + lane;
+    bool valid = r < P.n_rec;
+    const uint8_t* p = P.d;
+    uint32_t lseq = 0, f = 0, ncig = 0, lname = 0, mapq = 0, b = 0, uoff = 0;
+    int32_t ref = -1, pos = -1, nref = -1, tlen = 0;
+    if (valid) {
+      const uint64_t rv = P.rec[r];
+      b = (uint32_t)(rv >> 16);
+      uoff = (uint32_t)(rv & 0xFFFF);
+      p = P.d + P.out_off[b] + uoff;
+      // 36 header bytes at any alignment: ten aligned words, nine funnel shifts
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(3));
+      const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+      const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4], a5 = w[5], a6 = w[6], a7 = w[7], a8 = w[8], a9 = w[9];
+      const uint32_t bs = __funnelshift_r(a0, a1, sh);
+      ref = (int32_t)__funnelshift_r(a1, a2, sh);
+      pos = (int32_t)__funnelshift_r(a2, a3, sh);
+      const uint32_t w3 = __funnelshift_r(a3, a4, sh);
+      const uint32_t w4 = __funnelshift_r(a4, a5, sh);
+      lseq = __funnelshift_r(a5, a6, sh);
+      nref = (int32_t)__funnelshift_r(a6, a7, sh);
+      tlen = (int32_t)__funnelshift_r(a8, a9, sh);
+      lname = w3 & 255; mapq = (w3 >> 8) & 255; ncig = w4 & 0xFFFF; f = w4 >> 16;
+      const uint64_t need = 32ull + lname + 4ull * ncig + (lseq + 1ull) / 2 + lseq;
+      if (need > bs || ref < -1 || ref >= P.n_ref || nref < -1 || nref >= P.n_ref) { err_rec = 1; valid = false; }
+    }
     const uint8_t* cig = p + 36 + lname;
-    const uint8_t* seq = cig + 4 * ncig;
+    const uint8_t* seq = cig + 4 * (size_t)ncig;
     const uint8_t* qual = seq + (lseq + 1) / 2;
     const bool in_n = P.max_records == 0 || r < P.max_records;
-    const bool rec_on = do_rec && in_n;
+    const bool rec_on = valid && do_rec && in_n;
 
     // ---- CIGAR: kind tallies (general.rs:103-121) and reference span (utils/cigar.rs:6-11)
     uint32_t span = 0;
-    {
-      const uint32_t which = (f & 0x40) ? 0 : 9;
-      for (uint32_t i = lane; i < ncig; i += 32) {
-        uint32_t op = ld_u32_unaligned(cig + 4 * i);
-        uint32_t k = op & 15;
+    const uint32_t which = (f & 0x40) ? 0 : 9;
+    if (valid && ncig <= kShortCigar) {
+      for (uint32_t i = 0; i < ncig; ++i) {
+        const uint32_t op = ld_u32_unaligned(cig + 4 * i);
+        const uint32_t k = op & 15;
         if (k > 8) { err_rec = 1; continue; }
         if ((0x18D >> k) & 1) span += op >> 4;  // M D N = X
         if (rec_on) atomicAdd(&s_cig[(which + k) * 32 + lane], 1u);
       }
-      span = __reduce_add_sync(0xFFFFFFFFu, span);
+    }
+    // long CIGARs (long reads): the whole warp strides over one record's ops
+    for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, valid && ncig > kShortCigar); todo; todo &= todo - 1) {
+      const int j = __ffs(todo) - 1;
+      const uint8_t* cj = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)cig, j));
+      const uint32_t nj = __shfl_sync(0xFFFFFFFFu, ncig, j);
+      const uint32_t wj = __shfl_sync(0xFFFFFFFFu, which, j);
+      const bool onj = __shfl_sync(0xFFFFFFFFu, (int)rec_on, j);
+      uint32_t sp = 0, bad = 0;
+      for (uint32_t i = lane; i < nj; i += 32) {
+        const uint32_t op = ld_u32_unaligned(cj + 4 * i);
+        const uint32_t k = op & 15;
+        if (k > 8) { bad = 1; continue; }
+        if ((0x18D >> k) & 1) sp += op >> 4;
+        if (onj) atomicAdd(&s_cig[(wj + k) * 32 + lane], 1u);
+      }
+      sp = __reduce_add_sync(0xFFFFFFFFu, sp);
+      if (__any_sync(0xFFFFFFFFu, bad)) err_rec = 1;
+      if ((int)lane == j) span = sp;
     }
 
     // ---- Coverage scatter (coverage.rs:148-180 behind the query filter)
-    if (do_cov && lane == 0 && ref >= 0 && pos >= 0 && P.cov_enabled[ref]) {
+    if (do_cov && valid && ref >= 0 && pos >= 0 && P.cov_enabled[ref]) {
       const int64_t L = P.ref_len[ref];
       const int64_t start = (int64_t)pos + 1, end = start + (int64_t)span - 1;
       if (start <= L && end >= 1) {
@@ -137,98 +179,106 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
         }
       }
     }
-    if (!rec_on) continue;
+    if (!do_rec) continue;
 
     // ---- General counters (general.rs:31-101): bit k of `bits` increments counter k
-    uint32_t bits = 1u;
-    if (f & 0x4) bits |= 1u << 1;
-    if (f & 0x400) bits |= 1u << 2;
-    if (f & 0x100) bits |= 1u << 4;
-    else if (f & 0x800) bits |= 1u << 5;
-    else {
-      bits |= 1u << 3;
-      if (!(f & 0x4)) bits |= 1u << 6;
-      if (f & 0x400) bits |= 1u << 7;
-      if (f & 0x1) {
-        bits |= 1u << 8;
-        if (f & 0x40) bits |= 1u << 9;
-        if (f & 0x80) bits |= 1u << 10;
-        if (!(f & 0x4)) {
-          if (f & 0x2) bits |= 1u << 11;
-          if (f & 0x8) bits |= 1u << 12;
-          else {
-            bits |= 1u << 13;
-            if (ref < 0 || nref < 0) err_rec = 1;  // the reference panics here (general.rs:81-83)
-            else if (ref != nref) {
-              bits |= 1u << 14;
-              if (mapq >= 5) bits |= 1u << 15;     // missing (255) counts (general.rs:88-95)
+    uint32_t bits = 0;
+    bool gc_on = false;
+    uint32_t gc_off = 0;
+    if (rec_on) {
+      bits = 1u;
+      if (f & 0x4) bits |= 1u << 1;
+      if (f & 0x400) bits |= 1u << 2;
+      if (f & 0x100) bits |= 1u << 4;
+      else if (f & 0x800) bits |= 1u << 5;
+      else {
+        bits |= 1u << 3;
+        if (!(f & 0x4)) bits |= 1u << 6;
+        if (f & 0x400) bits |= 1u << 7;
+        if (f & 0x1) {
+          bits |= 1u << 8;
+          if (f & 0x40) bits |= 1u << 9;
+          if (f & 0x80) bits |= 1u << 10;
+          if (!(f & 0x4)) {
+            if (f & 0x2) bits |= 1u << 11;
+            if (f & 0x8) bits |= 1u << 12;
+            else {
+              bits |= 1u << 13;
+              if (ref < 0 || nref < 0) err_rec = 1;  // the reference panics here (general.rs:81-83)
+              else if (ref != nref) {
+                bits |= 1u << 14;
+                if (mapq >= 5) bits |= 1u << 15;     // missing (255) counts (general.rs:88-95)
+              }
             }
           }
         }
       }
-    }
-    // ---- Template length (template_length.rs:79-87): `tlen as usize`, bins 0..=1024
-    if (tlen >= 0 && tlen <= 1024) {
-      bits |= 1u << 16;
-      if (lane == 0) atomicAdd(&s_tlen[tlen], 1u);
-    } else bits |= 1u << 17;
-
-    // ---- GC content (gc_content.rs:38-100)
-    uint32_t gc = 0, at = 0, oth = 0;
-    if (f & (0x400 | 0x100)) bits |= 1u << 19;
-    else if (lseq < 100) bits |= 1u << 20;
-    else {
-      bits |= 1u << 18;
-      uint32_t offset = 0;
-      if (lseq > 100) {
-        const uint64_t voff = (P.coff[b] << 16) | uoff;
-        offset = (uint32_t)(((splitmix64_dev(P.gc_seed ^ voff) >> 32) * (uint64_t)(lseq - 100)) >> 32);
-      }
-#pragma unroll
-      for (uint32_t it = 0; it < 4; ++it) {
-        uint32_t i = it * 32 + lane;
-        if (i < 100) {
-          uint32_t k = offset + i;
-          uint32_t byte = __ldg(seq + (k >> 1));
-          uint32_t code = (k & 1) ? (byte & 15) : (byte >> 4);
-          gc += (code == 2) | (code == 4);
-          at += (code == 1) | (code == 8);
+      // ---- Template length (template_length.rs:79-87): `tlen as usize`, bins 0..=1024
+      if (tlen >= 0 && tlen <= 1024) {
+        bits |= 1u << 16;
+        atomicAdd(&s_tlen[tlen], 1u);
+      } else bits |= 1u << 17;
+      // ---- GC content eligibility (gc_content.rs:38-75)
+      if (f & (0x400 | 0x100)) bits |= 1u << 19;
+      else if (lseq < 100) bits |= 1u << 20;
+      else {
+        bits |= 1u << 18;
+        gc_on = true;
+        if (lseq > 100) {
+          const uint64_t voff = (P.coff[b] << 16) | uoff;
+          gc_off = (uint32_t)(((splitmix64_dev(P.gc_seed ^ voff) >> 32) * (uint64_t)(lseq - 100)) >> 32);
         }
       }
-      gc = __reduce_add_sync(0xFFFFFFFFu, gc);
-      at = __reduce_add_sync(0xFFFFFFFFu, at);
-      oth = 100 - gc - at;
-      if (lane == 0) atomicAdd(&s_gc[gc], 1u);  // round(gc/100*100) == gc
     }
-    uint32_t add = (bits >> lane) & 1u;
-    if (lane == 21) add = gc;
-    if (lane == 22) add = at;
-    if (lane == 23) add = oth;
-    acc += add;
+#pragma unroll
+    for (int k = 0; k < 21; ++k) {
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, (bits >> k) & 1u);
+      if ((int)lane == k) acc += __popc(m);
+    }
 
-    // ---- Quality scores (quality_scores.rs:37-49; presence rule SURVEY App. D.5)
-    if (lseq) {
-      bool any_real = false, any_bad = false;
-      for (uint32_t i = lane; i < lseq; i += 32) {
-        uint32_t q = __ldg(qual + i);
-        any_real |= q != 0xFF;
-        any_bad |= q > 93;
-      }
-      any_real = __any_sync(0xFFFFFFFFu, any_real);
-      any_bad = __any_sync(0xFFFFFFFFu, any_bad);
-      if (any_real) {
-        if (any_bad) err_qual = 1;
-        else {
-          max_qpos = lseq > max_qpos ? lseq : max_qpos;
-          const uint32_t n_sm_pos = lseq < P.qpos_smem ? lseq : P.qpos_smem;
-          for (uint32_t i = lane; i < n_sm_pos; i += 32) atomicAdd(&s_qual[i * 94 + __ldg(qual + i)], 1u);
-          if (lseq > P.qpos_smem) {
-            if (lseq > P.qpos_cap) err_rec = 1;
-            else
-              for (uint32_t i = P.qpos_smem + lane; i < lseq; i += 32)
-                atomicAdd((unsigned long long*)&P.qual[(uint64_t)i * 94 + __ldg(qual + i)], 1ull);
+    // ================= phase B: one record per warp step =================
+    for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, rec_on && lseq != 0); todo; todo &= todo - 1) {
+      const int j = __ffs(todo) - 1;
+      const uint8_t* sq = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)seq, j));
+      const uint32_t ls = __shfl_sync(0xFFFFFFFFu, lseq, j);
+      const uint8_t* ql = sq + (ls + 1) / 2;
+      const uint32_t gj = __shfl_sync(0xFFFFFFFFu, gc_on ? gc_off : 0xFFFFFFFFu, j);
+      // ---- GC window (gc_content.rs:76-100): 100 bases from the record's offset
+      if (gj != 0xFFFFFFFFu) {
+        uint32_t gc = 0, at = 0;
+#pragma unroll
+        for (uint32_t it = 0; it < 4; ++it) {
+          const uint32_t i = it * 32 + lane;
+          if (i < 100) {
+            const uint32_t k = gj + i;
+            const uint32_t byte = __ldg(sq + (k >> 1));
+            const uint32_t code = (k & 1) ? (byte & 15) : (byte >> 4);
+            gc += (code == 2) | (code == 4);
+            at += (code == 1) | (code == 8);
           }
         }
+        gc = __reduce_add_sync(0xFFFFFFFFu, gc);
+        at = __reduce_add_sync(0xFFFFFFFFu, at);
+        sum_gc += gc; sum_at += at; sum_oth += 100 - gc - at;
+        if (lane == 0) atomicAdd(&s_gc[gc], 1u);  // round(gc/100*100) == gc
+      }
+      // ---- Quality scores (quality_scores.rs:37-49; presence rule SURVEY App. D.5): one pass.
+      // Qualities are present unless every byte is 0xFF; a present string must be <= 93 throughout,
+      // so increments for bytes <= 93 are exact whenever the run does not fail.
+      bool any_real = false, any_big = false;
+      for (uint32_t i = lane; i < ls; i += 32) {
+        const uint32_t q = __ldg(ql + i);
+        any_real |= q != 0xFF;
+        if (q > 93) any_big = true;
+        else if (i < P.qpos_smem) atomicAdd(&s_qual[i * kQualStride + q], 1u);
+        else if (i < P.qpos_cap) atomicAdd((unsigned long long*)&P.qual[(uint64_t)i * 94 + q], 1ull);
+        else err_rec = 1;
+      }
+      any_real = __any_sync(0xFFFFFFFFu, any_real);
+      any_big = __any_sync(0xFFFFFFFFu, any_big);
+      if (any_real) {
+        if (any_big) err_qual = 1;
+        max_qpos = ls > max_qpos ? ls : max_qpos;
       }
     }
   }
@@ -236,18 +286,25 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
   // ---- flush ----
   __syncthreads();
   if (do_rec) {
-    // lane-owned counters: 0..15 general, 16/17 tlen processed/ignored, 18..20 gc records, 21..23 nucleobases
+    // lane-owned counters: 0..15 general, 16/17 tlen processed/ignored, 18..20 gc records
     if (acc) {
       uint32_t slot;
       if (lane < 16) slot = R_GENERAL + lane;
       else if (lane == 16) slot = R_TLEN_PROCESSED;
       else if (lane == 17) slot = R_TLEN_IGNORED;
-      else if (lane <= 20) slot = R_GC_REC + (lane - 18);
-      else slot = R_GC_NUC + (lane - 21);
-      if (lane < 24) atomicAdd((unsigned long long*)&P.res[slot], (unsigned long long)acc);
+      else slot = R_GC_REC + (lane - 18);
+      if (lane < 21) atomicAdd((unsigned long long*)&P.res[slot], (unsigned long long)acc);
     }
-    for (uint32_t i = threadIdx.x; i < P.qpos_smem * 94; i += blockDim.x)
-      if (s_qual[i]) atomicAdd((unsigned long long*)&P.qual[i], (unsigned long long)s_qual[i]);
+    if (lane == 0) {
+      if (sum_gc) atomicAdd((unsigned long long*)&P.res[R_GC_NUC + 0], (unsigned long long)sum_gc);
+      if (sum_at) atomicAdd((unsigned long long*)&P.res[R_GC_NUC + 1], (unsigned long long)sum_at);
+      if (sum_oth) atomicAdd((unsigned long long*)&P.res[R_GC_NUC + 2], (unsigned long long)sum_oth);
+    }
+    for (uint32_t i = threadIdx.x; i < P.qpos_smem * kQualStride; i += blockDim.x) {
+      const uint32_t v = s_qual[i];
+      const uint32_t qp = i / kQualStride, qs = i - qp * kQualStride;
+      if (v && qs < 94) atomicAdd((unsigned long long*)&P.qual[(uint64_t)qp * 94 + qs], (unsigned long long)v);
+    }
     for (uint32_t i = threadIdx.x; i < 1025; i += blockDim.x)
       if (s_tlen[i]) atomicAdd((unsigned long long*)&P.res[R_TLEN_HIST + i], (unsigned long long)s_tlen[i]);
     for (uint32_t i = threadIdx.x; i < 101; i += blockDim.x)

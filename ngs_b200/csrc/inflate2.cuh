@@ -79,21 +79,17 @@ __device__ __forceinline__ void store_bytes(uint8_t* d, uint2 v, uint32_t n) {  
   if (n > 7) d[7] = (uint8_t)(v.y >> 24);
 }
 
-// one lane copies one match; the source never includes bytes of the match itself (periodic extension)
+// One lane copies one match, 8 bytes per step.  A step copies from D bytes back, D a multiple of the
+// match distance: D = dist while dist >= 8; for shorter periods D doubles after every step (the
+// bytes written so far extend the periodic run), so overlapping runs need log2(8/dist) extra steps
+// instead of a byte loop.  Every step reads only final bytes or bytes this lane wrote earlier.
 __device__ __forceinline__ void resolve_copy(uint8_t* dst, uint32_t mlen, uint32_t dist) {
-  const uint8_t* src = dst - dist;
-  if (dist >= 8 || dist >= mlen) {
-    // 8 bytes per step: a step reads only final bytes or bytes this lane wrote in earlier steps
-    for (uint32_t k = 0; k < mlen; k += 8) store_bytes(dst + k, load8_unaligned(src + k), min(8u, mlen - k));
-  } else {
-    // overlapping run with a period below 8: replicate the period from registers
-    const uint2 pat = load8_unaligned(src);
-    const uint64_t P = (uint64_t)pat.x | ((uint64_t)pat.y << 32);
-    uint32_t ph = 0;
-    for (uint32_t k = 0; k < mlen; ++k) {
-      dst[k] = (uint8_t)(P >> (8 * ph));
-      ph = ph + 1 == dist ? 0 : ph + 1;
-    }
+  uint32_t D = dist;
+  for (uint32_t done = 0; done < mlen;) {
+    const uint32_t n = min(min(8u, D), mlen - done);
+    store_bytes(dst + done, load8_unaligned(dst + done - D), n);
+    done += n;
+    if (D < 8) D <<= 1;
   }
 }
 
@@ -129,23 +125,43 @@ inflate_resolve_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ 
         list[o++] = (uint16_t)(pbase + bit);
       }
       __syncwarp();
+      // token of the first batch; later batches are fetched one batch ahead (their bytes sit in
+      // their own destinations, which no earlier copy touches)
+      uint32_t pos_n = 0xFFFFu, tok_n = 0;
+      if (lane < total) {
+        pos_n = list[lane];
+        const uint8_t* t = ob + pos_n;
+        tok_n = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16);
+      }
       for (uint32_t base = 0; base < total; base += 32) {
-        const uint32_t j = base + lane;
-        const bool active = j < total;
-        uint32_t pos = 0, mlen = 0, dist = 1;
-        if (active) {
-          pos = list[j];
-          const uint8_t* t = ob + pos;
-          const uint32_t tok = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16);
-          mlen = (tok & 255u) + 3u;
-          dist = (tok >> 8) + 1u;
+        const bool active = base + lane < total;
+        const uint32_t pos = pos_n, tok = tok_n;
+        const uint32_t jn = base + 32 + lane;
+        if (jn < total) {
+          pos_n = list[jn];
+          const uint8_t* t = ob + pos_n;
+          tok_n = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16);
         }
-        const uint32_t src_end = pos - dist + min(mlen, dist);
+        const uint32_t mlen = (tok & 255u) + 3u, dist = (tok >> 8) + 1u;
+        // destinations [pos, dend) are ascending and disjoint across lanes (inactive lanes: empty at the top)
+        const uint32_t dpos = active ? pos : 0x20000u, dend = active ? pos + mlen : 0x20000u;
+        const uint32_t s_lo = pos - dist, s_hi = s_lo + min(mlen, dist);  // source bytes [s_lo, s_hi)
+        // earlier lanes whose destination overlaps my source: lanes [lo, hi) with
+        //   lo = first lane with dend > s_lo,  hi = first lane with dpos >= s_hi   (binary search by shuffle)
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int step = 32; step; step >>= 1) {
+          const uint32_t il = lo + step - 1, ih = hi + step - 1;
+          const uint32_t e = __shfl_sync(0xFFFFFFFFu, dend, il & 31);
+          const uint32_t p2 = __shfl_sync(0xFFFFFFFFu, dpos, ih & 31);
+          if (il < 32 && e <= s_lo) lo += step;
+          if (ih < 32 && p2 < s_hi) hi += step;
+        }
+        uint32_t dep = 0;
+        if (active && hi > lo) dep = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u) & ((1u << lane) - 1u);
         uint32_t done = __ballot_sync(0xFFFFFFFFu, !active);
         while (done != 0xFFFFFFFFu) {
-          const int f = __ffs(~done) - 1;
-          const uint32_t fpos = __shfl_sync(0xFFFFFFFFu, pos, f);
-          const bool ready = !((done >> lane) & 1u) && ((int)lane == f || src_end <= fpos);
+          const bool ready = !((done >> lane) & 1u) && (dep & ~done) == 0;
           if (ready) resolve_copy(ob + pos, mlen, dist);
           __syncwarp();
           done |= __ballot_sync(0xFFFFFFFFu, ready);
