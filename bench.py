@@ -40,7 +40,6 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--records", type=int, default=0, help="records per GPU (default 100M at N=1, 75M at N>1)")
     p.add_argument("--level", type=int, default=-1, help="zlib level of the synthetic BAM (default 1 for >=20M records, else 6)")
-    p.add_argument("--lanes", type=int, default=0, help="inflate group width (tuning)")
     p.add_argument("--chunk-mb", type=int, default=256, help="e2e submit chunk size")
     p.add_argument("--cpu-sample", type=int, default=3_000_000, help="records in the CPU-baseline sample")
     p.add_argument("--no-crc", action="store_true", help="skip the per-block CRC32 check (reference verifies it)")
@@ -208,7 +207,7 @@ def main():
     assert used == C_bytes
     flags = ffi.NGSQ_F_RECORD_FACETS | ffi.NGSQ_F_COVERAGE | (0 if args.no_crc else ffi.NGSQ_F_VERIFY_CRC)
     eng = ffi.Engine(device=local_rank, flags=flags, gc_seed=7, reserve_compressed=C_bytes, reserve_inflated=D_bytes + 65536,
-                     reserve_blocks=n_blocks + 16, inflate_lanes=args.lanes)
+                     reserve_blocks=n_blocks + 16)
     hdr = formats.read_header(eng, pinned)
     names = [n for n, _ in hdr.refs]
     lens = [l for _, l in hdr.refs]
@@ -263,11 +262,13 @@ def main():
     sampler.start()
     barrier()
     t0 = time.perf_counter()
-    dev_ms, infl_ms, stats = [], [], None
+    dev_ms, infl_ms, dec_ms_l, res_ms_l, stats = [], [], [], [], None
     for _ in range(args.steps):
         stats = step_resident()
         dev_ms.append(stats["ms_total"])
         infl_ms.append(stats["ms_inflate"])
+        dec_ms_l.append(stats["ms_inflate_decode"])
+        res_ms_l.append(stats["ms_inflate_resolve"])
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop()
@@ -303,7 +304,7 @@ def main():
         t0 = time.perf_counter()
         want = oracle_ints(sbam, sbai, gc_seed=7)
         cpu_s = time.perf_counter() - t0
-        got = engine_ints(sbam, gc_seed=7, device=local_rank, lanes=args.lanes)
+        got = engine_ints(sbam, gc_seed=7, device=local_rank)
         assert_same_ints(got, want)
         parity = "bit-exact vs oracle on the CPU-baseline sample (all integer outputs)"
         cpu = {"value": sn / cpu_s, "unit": "records/s", "cores": 1, "kind": "port",
@@ -312,12 +313,18 @@ def main():
     if rank == 0:
         peak, peak_kind = measured_peak()
         launches = max(stats["inflate_launches"], 1)
+        dec_ms = float(np.mean(dec_ms_l)) / launches   # average launch duration of the dominant kernel (CUDA events)
+        res_ms = float(np.mean(res_ms_l)) / launches
         infl_launch_ms = infl_ms_max / launches
-        achieved = (C_bytes + D_bytes) / (infl_launch_ms * 1e-3) / 1e9 if infl_launch_ms > 0 else 0.0
+        # algorithmic bytes of the decode kernel per launch: compressed bytes read + inflated bytes written
+        # (every 16-byte chunk is written once: literals, in-place match tokens, zeros elsewhere)
+        achieved = (C_bytes + D_bytes) / launches / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "inflate_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+                # ncu dram bytes per launch are proportional to the workload: scale from the profiled size
+                traffic = tj["decode_dram_bytes_per_inflated_byte"] * D_bytes / launches
         except Exception:
             pass
         A = all_C + 2 * all_D + sum(8 * (L + 2) for c, L in enumerate(lens) if formats.is_primary(names[c]))
@@ -331,12 +338,18 @@ def main():
             "config": {"workload": ("configs[1]: 100M-record 2x150bp WGS-shaped synthetic BAM, all facets incl. coverage" if N == 1 and per_gpu == 100_000_000
                                     else f"{int(all_rec)}-record 2x150bp WGS-shaped synthetic BAM partitioned by contig ranges over {N} GPU(s), all facets incl. coverage"),
                        "records": int(all_rec), "compressed_bytes": int(all_C), "inflated_bytes": int(all_D), "zlib_level": level,
-                       "crc_check": not args.no_crc, "inflate_lanes": args.lanes or 16,
+                       "crc_check": not args.no_crc,
                        "l2": "inputs (GBs) far exceed the 126 MB L2; no flush needed", "generation_s": gen_s,
-                       "stage_ms": {k: stats[k] for k in ["ms_inflate", "ms_crc", "ms_scan", "ms_facets", "ms_coverage"]}},
-            "roofline": {"bound": "hbm", "kernel": "inflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                       "stage_ms": {k: stats[k] for k in ["ms_inflate", "ms_inflate_decode", "ms_inflate_resolve", "ms_crc", "ms_scan", "ms_facets", "ms_coverage"]},
+                       "stage_gbs": {"inflate (C+D)/t": (C_bytes + D_bytes) / (stats["ms_inflate"] * 1e-3) / 1e9 if stats["ms_inflate"] else None,
+                                     "resolve D/t": D_bytes / (res_ms * launches * 1e-3) / 1e9 if res_ms else None,
+                                     "crc D/t": D_bytes / (stats["ms_crc"] * 1e-3) / 1e9 if stats["ms_crc"] else None,
+                                     "scan+facets D/t": D_bytes / ((stats["ms_scan"] + stats["ms_facets"]) * 1e-3) / 1e9,
+                                     "coverage 8*sum(L)/t": sum(8 * (L + 2) for c, L in enumerate(lens) if enabled[c]) / (stats["ms_coverage"] * 1e-3) / 1e9 if stats["ms_coverage"] else None}},
+            "roofline": {"bound": "hbm", "kernel": "inflate_decode_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_kind": peak_kind,
-                         "note": "algorithmic bytes = compressed read + inflated written per launch; DEFLATE decode is issue/latency-bound, not HBM-bound (DESIGN.md)"},
+                         "launch_ms": dec_ms,
+                         "note": "algorithmic bytes = compressed read + inflated written per launch; Huffman decode is instruction-issue bound, not HBM-bound (DESIGN.md section 4)"},
             "cpu_baseline": cpu,
             "e2e": None if args.no_e2e else {"value": all_rec / (e2e_ms_max * 1e-3), "unit": "records/s", "h2d_bytes_per_step": int(all_C),
                                              "d2h_bytes_per_step": int(8 * (1184 + 94 * 256 + sum(2052 + L // 50000 + 2 for L in lens))), "ms_per_step": e2e_ms_max},

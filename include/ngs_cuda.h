@@ -69,7 +69,8 @@ typedef struct ngsq_config {
   uint64_t reserve_compressed; /* optional upper bounds; 0 = grow on demand */
   uint64_t reserve_inflated;
   uint32_t reserve_blocks;
-  uint32_t inflate_lanes;      /* tuning: lanes cooperating on one BGZF block (4/8/16/32); 0 = default */
+  uint32_t launch_blocks;      /* tuning/testing: BGZF blocks per inflate launch of ngsq_submit; 0 = one wave of the
+                                  decode kernel (one block per lane, SMs x 512 lanes) */
 } ngsq_config;
 
 /* One BGZF block as framed by the host (K1). */
@@ -87,13 +88,15 @@ typedef struct ngsq_stats {
   uint64_t compressed_bytes; /* BGZF bytes submitted */
   uint64_t inflated_bytes;   /* sum of ISIZE */
   uint64_t max_read_len;     /* longest l_seq seen */
-  float ms_inflate;          /* device time of the inflate launches (CUDA events) */
+  float ms_inflate;          /* device time of the inflate launches (bitmap clear + decode + resolve; CUDA events) */
   float ms_crc;
   float ms_scan;             /* record-boundary discovery + offset table */
   float ms_facets;           /* fused record-facet + coverage-scatter kernel */
   float ms_coverage;         /* difference-array resolve */
   float ms_total;            /* first submit -> end of finish on the engine's stream */
   uint32_t inflate_launches, other_launches;
+  float ms_inflate_decode;   /* of ms_inflate: the lane-per-block Huffman decode kernel */
+  float ms_inflate_resolve;  /* of ms_inflate: the warp-per-block LZ77 resolve kernel */
 } ngsq_stats;
 
 int ngsq_version(void);
@@ -121,8 +124,10 @@ int ngsq_set_range(ngsq_engine* e, uint64_t first_rec_voffset, uint64_t end_voff
 int ngsq_bgzf_walk(const uint8_t* bgzf, size_t nbytes, uint64_t file_off, ngsq_block* out, uint32_t cap,
                    uint32_t* n_blocks, size_t* consumed);
 
-/* Streams one chunk of whole BGZF blocks from HOST memory: async H2D copy + inflate launch.
- * The buffer must stay valid until ngsq_finish returns.  Chunks must be submitted in file order. */
+/* Streams one chunk of whole BGZF blocks from HOST memory: async H2D copy; the inflate kernels are
+ * launched whenever a whole wave of blocks has been copied (and by ngsq_finish for the rest), so the
+ * copy of one chunk overlaps the kernels of the previous ones.  The buffer must stay valid until
+ * ngsq_finish returns.  Chunks must be submitted in file order. */
 int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t file_off);
 /* Same for a chunk already resident in DEVICE memory (used in place, not copied); the caller
  * passes the descriptors ngsq_bgzf_walk produced for it. */

@@ -20,7 +20,6 @@
 #include "coverage.cuh"
 #include "crc32.cuh"
 #include "facets.cuh"
-#include "inflate.cuh"
 #include "inflate2.cuh"
 #include "recscan.cuh"
 
@@ -76,12 +75,14 @@ bool load_nccl(std::string& err) {
 struct ngsq_engine {
   int device = 0;
   int n_sm = 0;
-  int inflate_occ = 0;
   ngsq_config cfg{};
   std::string err;
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
   std::vector<cudaEvent_t> copy_events;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> inflate_events;
+  std::vector<uint32_t> copy_upto;  // h_blocks.size() once the chunk of copy_events[i] was appended
+  uint32_t launched = 0;            // blocks [0, launched) have been handed to the inflate kernels
+  struct InflateEvents { cudaEvent_t begin, decoded_from, decoded, end; };
+  std::vector<InflateEvents> inflate_events;
   cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr, ev_f = nullptr;
   bool run_started = false, finished = false;
 
@@ -181,28 +182,9 @@ int grow(ngsq_engine* e, T*& ptr, size_t& cap, size_t need, size_t keep, cudaStr
   return NGSQ_OK;
 }
 
-template <int G>
-int launch_inflate_g(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_t* out, uint32_t* queue, uint32_t* status, cudaStream_t s) {
-  const size_t smem = (kInflateThreads / G) * sizeof(DecSmem);
-  if (!e->inflate_occ) {
-    int occ = 0;
-    CU(cudaFuncSetAttribute(inflate_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inflate_kernel<G>, kInflateThreads, smem));
-    e->inflate_occ = occ < 1 ? 1 : occ;
-  }
-  const int occ = e->inflate_occ;
-  uint32_t groups_per_cta = kInflateThreads / G;
-  uint32_t want = (n + groups_per_cta - 1) / groups_per_cta;
-  uint32_t grid = std::min<uint32_t>(want, (uint32_t)(e->n_sm * occ));
-  if (grid == 0) return NGSQ_OK;
-  inflate_kernel<G><<<grid, kInflateThreads, smem, s>>>(out, blocks, n, queue, status);
-  CU(cudaGetLastError());
-  return NGSQ_OK;
-}
-
-// v2: lane-per-block Huffman decode, then warp-per-block LZ77 resolve (inflate2.cuh)
-int launch_inflate_v2(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_t* out, uint32_t* queue, uint32_t* status,
-                      uint32_t* bitmap, cudaStream_t s) {
+// K2: lane-per-block Huffman decode, then warp-per-block LZ77 resolve (inflate2.cuh)
+int launch_inflate(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_t* out, uint32_t* queue, uint32_t* status,
+                   uint32_t* bitmap, cudaStream_t s, cudaEvent_t ev_decode_from = nullptr, cudaEvent_t ev_decoded = nullptr) {
   if (!n) return NGSQ_OK;
   static bool attr_set = false;
   if (!attr_set) {
@@ -212,21 +194,14 @@ int launch_inflate_v2(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8
   CU(cudaMemsetAsync(bitmap, 0, (size_t)n * kBitmapWords * 4, s));
   const uint32_t per_cta = kDecThreads;
   uint32_t grid = std::min<uint32_t>((n + per_cta - 1) / per_cta, (uint32_t)e->n_sm);
+  if (ev_decode_from) CU(cudaEventRecord(ev_decode_from, s));
   inflate_decode_kernel<<<grid, kDecThreads, kDecSmem, s>>>(out, blocks, n, queue, status, bitmap);
   CU(cudaGetLastError());
+  if (ev_decoded) CU(cudaEventRecord(ev_decoded, s));
   uint32_t rgrid = std::min<uint32_t>((n + kResWarps - 1) / kResWarps, (uint32_t)e->n_sm * 8);
   inflate_resolve_kernel<<<rgrid, kResThreads, 0, s>>>(out, blocks, n, bitmap, status);
   CU(cudaGetLastError());
   return NGSQ_OK;
-}
-
-int launch_inflate(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_t* out, uint32_t* queue, uint32_t* status, cudaStream_t s) {
-  switch (e->cfg.inflate_lanes) {
-    case 4: return launch_inflate_g<4>(e, blocks, n, out, queue, status, s);
-    case 8: return launch_inflate_g<8>(e, blocks, n, out, queue, status, s);
-    case 32: return launch_inflate_g<32>(e, blocks, n, out, queue, status, s);
-    default: return launch_inflate_g<16>(e, blocks, n, out, queue, status, s);
-  }
 }
 
 // The inflate kernel takes absolute device addresses in BlockDesc.in_off (comp == nullptr).
@@ -328,12 +303,11 @@ int inflate_new_blocks(ngsq_engine* e, uint32_t first_new, uint32_t n_new) {
   }
   CU(cudaMemcpyAsync(e->d_blocks + first_new, e->h_blocks.data() + first_new, n_new * sizeof(BlockDesc), cudaMemcpyHostToDevice, e->s_comp));
   if (e->n_launches >= ngsq_engine::kQueueSlots) return fail(e, NGSQ_E_ARG, "too many submits in one run (max %u)", ngsq_engine::kQueueSlots);
-  cudaEvent_t a, b;
-  CU(cudaEventCreate(&a));
-  CU(cudaEventCreate(&b));
-  CU(cudaEventRecord(a, e->s_comp));
+  ngsq_engine::InflateEvents ev{};
+  for (cudaEvent_t* x : {&ev.begin, &ev.decoded_from, &ev.decoded, &ev.end}) CU(cudaEventCreate(x));
+  CU(cudaEventRecord(ev.begin, e->s_comp));
   int rc;
-  if (e->cfg.inflate_lanes == 1) {
+  {
     if (total > e->bitmap_cap) {
       // earlier submits' bitmaps are dead once their resolve kernels ran: no need to keep them
       CU(cudaStreamSynchronize(e->s_comp));
@@ -344,17 +318,32 @@ int inflate_new_blocks(ngsq_engine* e, uint32_t first_new, uint32_t n_new) {
       if (r2 != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc match bitmap (%zu bytes): %s", cap * kBitmapWords * 4, cudaGetErrorString(r2));
       e->bitmap_cap = cap;
     }
-    rc = launch_inflate_v2(e, e->d_blocks + first_new, n_new, e->d_out, e->d_queue + e->n_launches, e->d_status + first_new,
-                           e->d_bitmap + (size_t)first_new * kBitmapWords, e->s_comp);
+    rc = launch_inflate(e, e->d_blocks + first_new, n_new, e->d_out, e->d_queue + e->n_launches, e->d_status + first_new,
+                        e->d_bitmap + (size_t)first_new * kBitmapWords, e->s_comp, ev.decoded_from, ev.decoded);
     e->other_launches += 1;  // resolve kernel (the decode kernel is counted as the inflate launch)
-  } else {
-    rc = launch_inflate(e, e->d_blocks + first_new, n_new, e->d_out, e->d_queue + e->n_launches, e->d_status + first_new, e->s_comp);
   }
   if (rc) return rc;
-  CU(cudaEventRecord(b, e->s_comp));
-  e->inflate_events.push_back({a, b});
+  CU(cudaEventRecord(ev.end, e->s_comp));
+  e->inflate_events.push_back(ev);
   e->n_launches++;
   return NGSQ_OK;
+}
+
+// Hands blocks [launched, upto) to the inflate kernels.  Launches are sized in whole waves of the
+// decode kernel (one BGZF block per lane, n_sm x kDecThreads lanes): a launch takes the time of its
+// slowest lane, so many small launches would each pay a full block-decode latency.
+int launch_pending(ngsq_engine* e, uint32_t upto) {
+  if (upto <= e->launched) return NGSQ_OK;
+  for (size_t i = 0; i < e->copy_upto.size(); ++i)
+    if (e->copy_upto[i] >= upto) { CU(cudaStreamWaitEvent(e->s_comp, e->copy_events[i], 0)); break; }
+  int rc = inflate_new_blocks(e, e->launched, upto - e->launched);
+  if (rc) return rc;
+  e->launched = upto;
+  return NGSQ_OK;
+}
+
+uint32_t launch_quantum(const ngsq_engine* e) {
+  return e->cfg.launch_blocks ? e->cfg.launch_blocks : (uint32_t)e->n_sm * kDecThreads;
 }
 
 }  // namespace
@@ -378,8 +367,6 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   ne->device = device;
   if (cfg) memcpy(&ne->cfg, cfg, std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(ngsq_config), sizeof(ngsq_config)));
   if (!ne->cfg.flags) ne->cfg.flags = NGSQ_F_RECORD_FACETS | NGSQ_F_COVERAGE;
-  // 0 / 1 = v2 (lane-per-block decode + warp-per-block resolve); 4/8/16/32 = v1 group-per-block kernel (kept for A/B runs)
-  if (ne->cfg.inflate_lanes != 4 && ne->cfg.inflate_lanes != 8 && ne->cfg.inflate_lanes != 16 && ne->cfg.inflate_lanes != 32) ne->cfg.inflate_lanes = 1;
   e = ne;
   auto bail = [&](int code) { std::string m = e->err; ngsq_destroy(e); g_create_err = m; return code; };
 #define CUC(call) do { cudaError_t _r = (call); if (_r != cudaSuccess) { fail(e, NGSQ_E_CUDA, "%s: %s", #call, cudaGetErrorString(_r)); return bail(NGSQ_E_CUDA); } } while (0)
@@ -393,6 +380,7 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   CUC(cudaMalloc(&e->d_queue, ngsq_engine::kQueueSlots * 4));
   CUC(cudaMalloc(&e->d_flags, sizeof(DevFlags)));
   CUC(cudaMalloc(&e->d_crc_tables, sizeof(CrcTables)));
+  CUC(cudaFuncSetAttribute(crc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCrcSmem));
   {
     CrcTables t;
     crc_make_tables(t);
@@ -425,7 +413,7 @@ void ngsq_destroy(ngsq_engine* e) {
   cudaDeviceSynchronize();
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto ev : e->copy_events) cudaEventDestroy(ev);
-  for (auto& p : e->inflate_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto& p : e->inflate_events) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.end}) cudaEventDestroy(x);
   for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_c, e->ev_d, e->ev_e, e->ev_f}) if (ev) cudaEventDestroy(ev);
   void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_res, e->d_out,
                   e->d_blocks, e->d_status, e->d_bitmap, e->d_queue, e->d_out_off, e->d_coff, e->d_base, e->d_rec, e->d_first, e->d_landed,
@@ -444,7 +432,9 @@ int ngsq_reset(ngsq_engine* e) {
   CU(cudaStreamSynchronize(e->s_comp));
   for (auto ev : e->copy_events) cudaEventDestroy(ev);
   e->copy_events.clear();
-  for (auto& p : e->inflate_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  e->copy_upto.clear();
+  e->launched = 0;
+  for (auto& p : e->inflate_events) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.end}) cudaEventDestroy(x);
   e->inflate_events.clear();
   e->h_blocks.clear(); e->h_coff.clear(); e->h_out_off.clear(); e->h_crc.clear();
   // keep the largest compressed segment, drop the rest
@@ -587,8 +577,11 @@ int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t fil
   uint32_t first_new, n_new;
   rc = append_blocks(e, blk.data(), n, (uint64_t)(uintptr_t)dst, file_off, &first_new, &n_new);
   if (rc) return rc;
-  CU(cudaStreamWaitEvent(e->s_comp, ev, 0));
-  return inflate_new_blocks(e, first_new, n_new);
+  e->copy_upto.push_back((uint32_t)e->h_blocks.size());
+  // inflate in whole waves; the copy of the next chunk overlaps the kernels of this one
+  const uint32_t quantum = launch_quantum(e), pending = (uint32_t)e->h_blocks.size() - e->launched;
+  if (pending >= quantum) return launch_pending(e, e->launched + pending / quantum * quantum);
+  return NGSQ_OK;
 }
 
 int ngsq_submit_device(ngsq_engine* e, const void* dev_bgzf, size_t nbytes, const ngsq_block* blocks, uint32_t n_blocks) {
@@ -604,7 +597,8 @@ int ngsq_submit_device(ngsq_engine* e, const void* dev_bgzf, size_t nbytes, cons
   uint32_t first_new, n_new;
   rc = append_blocks(e, blocks, n_blocks, (uint64_t)(uintptr_t)dev_bgzf, blocks[0].coffset, &first_new, &n_new);
   if (rc) return rc;
-  return inflate_new_blocks(e, first_new, n_new);
+  // resident data: one persistent launch over everything submitted so far (its block queue balances the lanes)
+  return launch_pending(e, (uint32_t)e->h_blocks.size());
 }
 
 static int voff_to_off(ngsq_engine* e, uint64_t voff, uint64_t* off) {
@@ -631,6 +625,8 @@ int ngsq_finish(ngsq_engine* e) {
   if (e->finished) return NGSQ_OK;
   CU(cudaSetDevice(e->device));
   int rc = start_run(e);
+  if (rc) return rc;
+  rc = launch_pending(e, (uint32_t)e->h_blocks.size());
   if (rc) return rc;
   cudaStream_t s = e->s_comp;
   const uint32_t nb = (uint32_t)e->h_blocks.size();
@@ -666,7 +662,7 @@ int ngsq_finish(ngsq_engine* e) {
     // CRC (optional, reference behaviour)
     if (e->cfg.flags & NGSQ_F_VERIFY_CRC) {
       CU(cudaMemcpyAsync(e->d_crc, e->h_crc.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, s));
-      crc32_kernel<<<e->n_sm * 8, 256, 0, s>>>(e->d_out, e->d_blocks, e->d_crc, nb, e->d_crc_tables, &e->d_flags->crc_bad);
+      crc32_kernel<<<e->n_sm * 6, kCrcThreads, kCrcSmem, s>>>(e->d_out, e->d_blocks, e->d_crc, nb, e->d_crc_tables, &e->d_flags->crc_bad);
       CU(cudaGetLastError());
       e->other_launches++;
     }
@@ -780,7 +776,14 @@ int ngsq_finish(ngsq_engine* e) {
   ngsq_stats& st = e->stats;
   st.records = n_rec; st.blocks = nb; st.compressed_bytes = e->comp_bytes_total; st.inflated_bytes = d_end; st.max_read_len = max_lseq;
   st.ms_inflate = 0;
-  for (auto& p : e->inflate_events) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); st.ms_inflate += ms; }
+  st.ms_inflate_decode = 0;
+  st.ms_inflate_resolve = 0;
+  for (auto& p : e->inflate_events) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p.begin, p.end); st.ms_inflate += ms;
+    cudaEventElapsedTime(&ms, p.decoded_from, p.decoded); st.ms_inflate_decode += ms;
+    cudaEventElapsedTime(&ms, p.decoded, p.end); st.ms_inflate_resolve += ms;
+  }
   cudaEventElapsedTime(&st.ms_crc, e->ev_a, e->ev_b);
   cudaEventElapsedTime(&st.ms_scan, e->ev_b, e->ev_c);
   cudaEventElapsedTime(&st.ms_facets, e->ev_c, e->ev_d);
@@ -985,12 +988,8 @@ int ngsq_inflate_to_host(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uin
     CU(cudaMemcpyAsync(d_in, bgzf, used, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_b, hb.data(), hb.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, s));
     uint32_t* d_bm = nullptr;
-    if (e->cfg.inflate_lanes == 1) {
-      CU(cudaMalloc(&d_bm, hb.size() * kBitmapWords * 4));
-      ret = launch_inflate_v2(e, d_b, (uint32_t)hb.size(), d_o, d_q, d_st, d_bm, s);
-    } else {
-      ret = launch_inflate(e, d_b, (uint32_t)hb.size(), d_o, d_q, d_st, s);
-    }
+    CU(cudaMalloc(&d_bm, hb.size() * kBitmapWords * 4));
+    ret = launch_inflate(e, d_b, (uint32_t)hb.size(), d_o, d_q, d_st, d_bm, s);
     std::vector<uint32_t> st(hb.size());
     if (!ret) {
       CU(cudaMemcpyAsync(out, d_o, total, cudaMemcpyDeviceToHost, s));

@@ -46,7 +46,7 @@ class Config(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("flags", C.c_uint32), ("gc_seed", C.c_uint64), ("max_records", C.c_uint64),
         ("reserve_compressed", C.c_uint64), ("reserve_inflated", C.c_uint64), ("reserve_blocks", C.c_uint32),
-        ("inflate_lanes", C.c_uint32),
+        ("launch_blocks", C.c_uint32),
     ]
 
 
@@ -60,7 +60,7 @@ class Stats(C.Structure):
         ("records", C.c_uint64), ("blocks", C.c_uint64), ("compressed_bytes", C.c_uint64), ("inflated_bytes", C.c_uint64),
         ("max_read_len", C.c_uint64), ("ms_inflate", C.c_float), ("ms_crc", C.c_float), ("ms_scan", C.c_float),
         ("ms_facets", C.c_float), ("ms_coverage", C.c_float), ("ms_total", C.c_float), ("inflate_launches", C.c_uint32),
-        ("other_launches", C.c_uint32),
+        ("other_launches", C.c_uint32), ("ms_inflate_decode", C.c_float), ("ms_inflate_resolve", C.c_float),
     ]
 
     def as_dict(self):
@@ -148,10 +148,10 @@ class Engine:
 
     def __init__(self, device: int = 0, flags: int = NGSQ_F_RECORD_FACETS | NGSQ_F_COVERAGE, gc_seed: int = 0,
                  max_records: int = 0, reserve_compressed: int = 0, reserve_inflated: int = 0, reserve_blocks: int = 0,
-                 inflate_lanes: int = 0):
+                 launch_blocks: int = 0):
         self.lib = load_library()
         cfg = Config(C.sizeof(Config), flags, gc_seed, max_records, reserve_compressed, reserve_inflated, reserve_blocks,
-                     inflate_lanes)
+                     launch_blocks)
         h = C.c_void_p()
         rc = self.lib.ngsq_create(device, C.byref(cfg), C.byref(h))
         if rc:

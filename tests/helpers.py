@@ -112,12 +112,12 @@ def oracle_ints(bam: np.ndarray, bai: np.ndarray, n_records=0, gc_seed=0, record
     return out
 
 
-def engine_ints(bam: np.ndarray, n_records=0, gc_seed=0, records=True, coverage=True, chunk_bytes=None, lanes=0,
+def engine_ints(bam: np.ndarray, n_records=0, gc_seed=0, records=True, coverage=True, chunk_bytes=None, launch_blocks=0,
                 crc=True, device=0, shard=None, engine=None):
     """Pushes a whole BAM (or one shard of it) through the C ABI; returns integers + stats."""
     from ngs_b200 import ffi, formats
     flags = (ffi.NGSQ_F_RECORD_FACETS if records else 0) | (ffi.NGSQ_F_COVERAGE if coverage else 0) | (ffi.NGSQ_F_VERIFY_CRC if crc else 0)
-    eng = engine or ffi.Engine(device=device, flags=flags, gc_seed=gc_seed, max_records=n_records, inflate_lanes=lanes)
+    eng = engine or ffi.Engine(device=device, flags=flags, gc_seed=gc_seed, max_records=n_records, launch_blocks=launch_blocks)
     hdr = formats.read_header(eng, bam)
     names = [n for n, _ in hdr.refs]
     lens = [l for _, l in hdr.refs]

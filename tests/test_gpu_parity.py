@@ -26,11 +26,12 @@ def test_inflate_bytes_match_zlib(level):
     np.testing.assert_array_equal(got, want)
 
 
-@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
-def test_inflate_group_widths(lanes):
+@pytest.mark.parametrize("shape,n,level", [(1, 40000, 1), (2, 400, 6), (3, 30000, 1), (3, 30000, 9)])
+def test_inflate_bytes_other_shapes(shape, n, level):
+    """K2 on the WGS, long-read and RNA-seq shapes (different literal/match mixes and match lengths)."""
     from ngs_b200 import ffi
-    bam, _, info = _synth(0, 30000)
-    eng = ffi.Engine(inflate_lanes=lanes)
+    bam, _, info = _synth(shape, n, level=level)
+    eng = ffi.Engine()
     got = eng.inflate_to_host(bam)
     want = np.empty(info["inflated_bytes"], dtype=np.uint8)
     oracle_lib().oracle_inflate_all(bam.ctypes.data, bam.size, want.ctypes.data, want.size)
@@ -49,7 +50,7 @@ def test_all_facets_match_oracle(shape, n):
 def test_chunked_submit_matches_single_submit():
     bam, bai, _ = _synth(0, 150000)
     want = oracle_ints(bam, bai, gc_seed=1)
-    got = engine_ints(bam, gc_seed=1, chunk_bytes=1 << 20)
+    got = engine_ints(bam, gc_seed=1, chunk_bytes=1 << 20, launch_blocks=64)
     assert got["stats"]["inflate_launches"] > 4
     assert_same_ints(got, want)
 

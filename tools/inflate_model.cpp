@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "../ngs_b200/csrc/inflate_lane.cuh"
@@ -33,7 +34,7 @@ int main(int argc, char** argv) {
   std::vector<uint32_t> bitmap(kBitmapWords);
   std::vector<uint8_t> out(65536 + 64), ref(65536);
   uint64_t hist_len[260] = {0}, n_blocks = 0, total_out = 0, total_in = 0, bad = 0, resolve_tokens = 0;
-  uint64_t dist_small = 0, dist_lt_len = 0;
+  uint64_t dist_small = 0, dist_lt_len = 0, rounds_hist[34] = {0}, n_batches = 0, rounds_total = 0;
   size_t o = 0;
   while (o + 18 <= n && n_blocks < max_blocks) {
     const uint8_t* h = &buf[o];
@@ -73,6 +74,36 @@ int main(int argc, char** argv) {
         uint8_t* ob = out.data() + d.out_off;
         for (int g = 1; g <= 4; ++g)
           if (ob[-g] != 0xAA || ob[isize + g - 1] != 0xAA) { fprintf(stderr, "block at %zu: wrote outside (mis %d)\n", o, mis); bad++; }
+        // dependency depth of the resolve kernel's 32-token batches (per 1024-byte super-window)
+        if (mis == 0) {
+          for (uint32_t sw = 0; sw < kBitmapWords / 32; ++sw) {
+            std::vector<uint32_t> ps;
+            for (uint32_t w = sw * 32; w < sw * 32 + 32; ++w)
+              for (uint32_t m = bitmap[w]; m; m &= m - 1) ps.push_back(w * 32 + __builtin_ctz(m));
+            for (size_t base = 0; base < ps.size(); base += 32) {
+              size_t nb = std::min<size_t>(32, ps.size() - base);
+              uint32_t depth[32], maxd = 0;
+              for (size_t j = 0; j < nb; ++j) {
+                uint32_t pj = ps[base + j];
+                uint32_t tok = ob[pj] | (ob[pj + 1] << 8) | (ob[pj + 2] << 16);
+                uint32_t ml = (tok & 255) + 3, di = (tok >> 8) + 1;
+                uint32_t slo = pj - di, shi = slo + std::min(ml, di);
+                uint32_t dj = 1;
+                for (size_t i = 0; i < j; ++i) {
+                  uint32_t pi = ps[base + i];
+                  uint32_t ti = ob[pi] | (ob[pi + 1] << 8) | (ob[pi + 2] << 16);
+                  uint32_t mi = (ti & 255) + 3;
+                  if (pi + mi > slo && pi < shi) dj = std::max(dj, depth[i] + 1);
+                }
+                depth[j] = dj;
+                maxd = std::max(maxd, dj);
+              }
+              rounds_hist[std::min<uint32_t>(maxd, 33)]++;
+              n_batches++;
+              rounds_total += maxd;
+            }
+          }
+        }
         // resolve pass (scalar, stream order)
         for (uint32_t w = 0; w < kBitmapWords; ++w) {
           uint32_t m = bitmap[w];
@@ -128,6 +159,9 @@ int main(int argc, char** argv) {
   printf("stores: %llu chunk + %llu edge = %.3f per output byte\n", (unsigned long long)ctr.chunk_stores, (unsigned long long)ctr.edge_stores,
          (double)(ctr.chunk_stores + ctr.edge_stores) / total_out);
   printf("dist<4: %.1f%% of matches, dist<len: %.1f%%\n", 100.0 * dist_small / (resolve_tokens ? resolve_tokens : 1), 100.0 * dist_lt_len / (resolve_tokens ? resolve_tokens : 1));
+  printf("resolve batches %llu, mean dependency depth %.2f; depth histogram %%:", (unsigned long long)n_batches, (double)rounds_total / (n_batches ? n_batches : 1));
+  for (int d = 1; d <= 33; ++d) if (rounds_hist[d]) printf(" %d:%.1f", d, 100.0 * rounds_hist[d] / n_batches);
+  printf("\n");
   printf("match length histogram (cumulative %%):");
   uint64_t cum = 0;
   for (int l = 3; l <= 258; ++l) {

@@ -6,11 +6,10 @@ import numpy as np
 from ngs_b200 import ffi, formats
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
-lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-level = int(sys.argv[3]) if len(sys.argv) > 3 else 6
-reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+level = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 bam, bai, info = ffi.synth_bam(1, n, level=level)
-eng = ffi.Engine(flags=7, gc_seed=7, inflate_lanes=lanes, reserve_compressed=bam.size, reserve_inflated=info["inflated_bytes"] + 65536, reserve_blocks=info["n_blocks"] + 16)
+eng = ffi.Engine(flags=7, gc_seed=7, reserve_compressed=bam.size, reserve_inflated=info["inflated_bytes"] + 65536, reserve_blocks=info["n_blocks"] + 16)
 hdr = formats.read_header(eng, bam)
 eng.set_references([l for _, l in hdr.refs], [1 if formats.is_primary(nm) else 0 for nm, _ in hdr.refs])
 eng.set_range(hdr.first_voffset, 0)
