@@ -150,6 +150,14 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """Progress on stderr (stdout carries only the JSON line): makes a hang on a GPU box diagnosable."""
+    print(f"[bench r{os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -172,6 +180,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     N = args.gpus
     if N > 1:
+        log("init_process_group")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -192,6 +201,7 @@ def main():
     t0 = time.perf_counter()
     bam, bai, info = ffi.synth_bam(shape, total_records, level=level, contig_mask=mask, with_tail=(rank == tail_rank))
     gen_s = time.perf_counter() - t0
+    log(f"generated shard: {info['n_records']} records, {bam.size} bytes in {gen_s:.1f}s")
     n_rec = info["n_records"]
     C_bytes, D_bytes = int(bam.size), int(info["inflated_bytes"])
 
@@ -211,19 +221,23 @@ def main():
     hdr = formats.read_header(eng, pinned)
     names = [n for n, _ in hdr.refs]
     lens = [l for _, l in hdr.refs]
-    enabled = [1 if (formats.is_primary(nm) and c in parts[rank]) else 0 for c, nm in enumerate(names)]
+    # the same coverage mask on every rank: the packed result layout (the NCCL payload) depends on it;
+    # contigs a rank does not own stay untouched there and contribute zeros to the reduce
+    enabled = [1 if formats.is_primary(nm) else 0 for nm in names]
     eng.set_references(lens, enabled)
     eng.set_range(hdr.first_voffset, 0)
     d_comp = torch.empty(C_bytes + 512, dtype=torch.uint8, device=dev)
     d_comp[:C_bytes].copy_(torch.from_numpy(pinned))
     torch.cuda.synchronize()
 
+    log("engine ready, compressed shard resident")
     if N > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(ffi.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         eng.comm_init(N, rank, bytes(uid.cpu().numpy().tobytes()))
+        log("engine NCCL communicator ready")
 
     def step_resident():
         eng.reset()
@@ -255,8 +269,9 @@ def main():
         return res
 
     # ---- warm-up ----
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
+    for i in range(max(args.warmup, 3)):
+        st = step_resident()
+        log(f"warm-up {i}: {st['ms_total']:.1f} ms")
     # ---- timed: device-resident ----
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -265,7 +280,7 @@ def main():
     dev_ms, infl_ms, dec_ms_l, res_ms_l, stats = [], [], [], [], None
     for _ in range(args.steps):
         stats = step_resident()
-        dev_ms.append(stats["ms_total"])
+        dev_ms.append(stats["ms_total"] + stats["ms_reduce"])
         infl_ms.append(stats["ms_inflate"])
         dec_ms_l.append(stats["ms_inflate_decode"])
         res_ms_l.append(stats["ms_inflate_resolve"])
@@ -275,6 +290,7 @@ def main():
     dev_step_ms = float(np.mean(dev_ms))
 
     # ---- timed: end to end from pinned host memory ----
+    log(f"resident steps done: {dev_step_ms:.1f} ms/step")
     e2e_ms = None
     res = None
     if not args.no_e2e:
@@ -286,6 +302,7 @@ def main():
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
 
+    log("e2e steps done")
     # ---- max over ranks ----
     agg = torch.tensor([dev_step_ms, wall_ms, e2e_ms or 0.0, float(np.mean(infl_ms))], dtype=torch.float64, device=dev)
     tot = torch.tensor([n_rec, C_bytes, D_bytes], dtype=torch.float64, device=dev)
@@ -298,6 +315,27 @@ def main():
     # ---- parity + CPU baseline on a bounded sample (rank 0) ----
     cpu = None
     parity = None
+    merged_parity = None
+    if N > 1 and not args.no_cpu:
+        # N-rank parity: the same contig-exclusive partition + the engine's NCCL reduce on a small logical
+        # BAM must reproduce the oracle's whole-file integers (coverage included) on rank 0
+        sn = args.cpu_sample
+        per_s, _ = ffi.synth_layout(shape, sn)
+        parts_s, loads_s = lpt_partition(per_s, N)
+        mask_s = sum(1 << c for c in parts_s[rank])
+        sb, _, _ = ffi.synth_bam(shape, sn, level=6, contig_mask=mask_s, with_tail=(rank == int(np.argmin(loads_s))))
+        hdr_s = formats.read_header(eng, sb)
+        eng.reset()
+        eng.set_range(hdr_s.first_voffset, 0)
+        eng.submit(sb, 0)
+        eng.finish()
+        eng.reduce(0)
+        if rank == 0:
+            got_m = collect(eng, lens, enabled)
+            wb, wbai, _ = ffi.synth_bam(shape, sn, level=6)
+            assert_same_ints(got_m, oracle_ints(wb, wbai, gc_seed=7))
+            merged_parity = f"{N}-rank shards + NCCL reduce bit-exact vs oracle on the whole {sn}-record sample"
+        log("merged parity checked")
     if rank == 0 and not args.no_cpu:
         sn = args.cpu_sample
         sbam, sbai, sinfo = ffi.synth_bam(shape, sn, level=6)
@@ -354,7 +392,7 @@ def main():
             "e2e": None if args.no_e2e else {"value": all_rec / (e2e_ms_max * 1e-3), "unit": "records/s", "h2d_bytes_per_step": int(all_C),
                                              "d2h_bytes_per_step": int(8 * (1184 + 94 * 256 + sum(2052 + L // 50000 + 2 for L in lens))), "ms_per_step": e2e_ms_max},
             "gpu_launches": int((stats["inflate_launches"] + stats["other_launches"]) * args.steps),
-            "clocks": clocks, "parity": parity,
+            "clocks": clocks, "parity": parity, "merged_parity": merged_parity,
         }
         print(json.dumps(line), flush=True)
     lib.ngsq_host_free(pin_ptr)

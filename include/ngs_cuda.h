@@ -97,6 +97,7 @@ typedef struct ngsq_stats {
   uint32_t inflate_launches, other_launches;
   float ms_inflate_decode;   /* of ms_inflate: the lane-per-block Huffman decode kernel */
   float ms_inflate_resolve;  /* of ms_inflate: the warp-per-block LZ77 resolve kernel */
+  float ms_reduce;           /* ngsq_reduce: agreement all-reduce + sum-reduce + refresh (0 without it) */
 } ngsq_stats;
 
 int ngsq_version(void);

@@ -125,6 +125,7 @@ struct ngsq_engine {
   uint32_t* d_bitmap = nullptr;  // v2 inflate: one bit per inflated byte, kBitmapWords per block
   size_t bitmap_cap = 0;         // blocks
   uint32_t* d_queue = nullptr;
+  uint64_t* d_agree = nullptr;  // 3 words exchanged before the reduce
   uint32_t n_launches = 0;
   static constexpr uint32_t kQueueSlots = 4096;
   uint64_t *d_out_off = nullptr, *d_coff = nullptr, *d_base = nullptr, *d_rec = nullptr;
@@ -416,7 +417,7 @@ void ngsq_destroy(ngsq_engine* e) {
   for (auto& p : e->inflate_events) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.end}) cudaEventDestroy(x);
   for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_c, e->ev_d, e->ev_e, e->ev_f}) if (ev) cudaEventDestroy(ev);
   void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_res, e->d_out,
-                  e->d_blocks, e->d_status, e->d_bitmap, e->d_queue, e->d_out_off, e->d_coff, e->d_base, e->d_rec, e->d_first, e->d_landed,
+                  e->d_blocks, e->d_status, e->d_bitmap, e->d_queue, e->d_agree, e->d_out_off, e->d_coff, e->d_base, e->d_rec, e->d_first, e->d_landed,
                   e->d_count, e->d_crc, e->d_flags, e->d_crc_tables};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& sg : e->comp_segs) cudaFree(sg.ptr);
@@ -738,7 +739,7 @@ int ngsq_finish(ngsq_engine* e) {
     P.res = e->d_res; P.qual = e->d_res + e->qual_off;
     P.qpos_smem = std::min<uint32_t>(std::max<uint32_t>(max_lseq, 1), 256);
     P.qpos_cap = e->qpos_cap;
-    size_t smem = ((size_t)P.qpos_smem * kQualStride + kTlenPad + kGcPad + kCigWords) * 4;
+    size_t smem = ((size_t)qual_rows(P.qpos_smem) * kQualStride + kTlenPad + kGcPad + kCigWords) * 4;
     CU(cudaFuncSetAttribute(facets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, facets_kernel, kFacetThreads, smem));
@@ -919,25 +920,37 @@ int ngsq_reduce(ngsq_engine* e, int root) {
   if (!e->comm) return fail(e, NGSQ_E_NCCL, "ngsq_comm_init was not called");
   CU(cudaSetDevice(e->device));
   cudaStream_t s = e->s_comp;
-  // agree on the quality table size: max over ranks of the longest read with qualities
-  uint64_t* d_q = e->d_res + R_QUAL_POSITIONS;
+  CU(cudaEventRecord(e->ev_a, s));
+  // agree on the quality table size (max over ranks of the longest read with qualities) and check
+  // that every rank packs the same layout: a count mismatch would hang the reduce
+  if (!e->d_agree) CU(cudaMalloc(&e->d_agree, 3 * 8));
   const int ncclUint64 = 5, ncclSum = 0, ncclMax = 2;
-  int rc = g_nccl.AllReduce(d_q, d_q, 1, ncclUint64, ncclMax, e->comm, s);
+  const uint64_t layout = e->qual_off;
+  uint64_t agree[3] = {e->h_res[R_QUAL_POSITIONS], layout, ~layout};
+  CU(cudaMemcpyAsync(e->d_agree, agree, sizeof agree, cudaMemcpyHostToDevice, s));
+  int rc = g_nccl.AllReduce(e->d_agree, e->d_agree, 3, ncclUint64, ncclMax, e->comm, s);
   if (rc) return fail(e, NGSQ_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
-  uint64_t qmax = 0;
-  CU(cudaMemcpyAsync(&qmax, d_q, 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(agree, e->d_agree, sizeof agree, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  if (agree[1] != layout || ~agree[2] != layout)
+    return fail(e, NGSQ_E_ARG, "result layouts differ across ranks: ngsq_set_references must get the same lengths and coverage mask on every rank");
+  const uint64_t qmax = agree[0];
   rc = ensure_res(e, (uint32_t)qmax, true);
   if (rc) return rc;
   // the max word must not be summed: park it, reduce, restore
   CU(cudaMemsetAsync(e->d_res + R_QUAL_POSITIONS, 0, 8, s));
-  rc = g_nccl.Reduce(e->d_res, e->d_res, e->res_words, ncclUint64, ncclSum, root, e->comm, s);
+  // the same count on every rank (a rank may hold a larger table from an earlier run)
+  const size_t n_words = (size_t)e->qual_off + (size_t)std::max<uint64_t>(qmax, 256) * 94;
+  rc = g_nccl.Reduce(e->d_res, e->d_res, n_words, ncclUint64, ncclSum, root, e->comm, s);
   if (rc) return fail(e, NGSQ_E_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
   CU(cudaMemcpyAsync(e->d_res + R_QUAL_POSITIONS, &qmax, 8, cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));
   e->other_launches += 2;
   rc = ngsq_refresh_results(e);
   if (rc) return rc;
+  CU(cudaEventRecord(e->ev_b, s));
+  CU(cudaEventSynchronize(e->ev_b));
+  cudaEventElapsedTime(&e->stats.ms_reduce, e->ev_a, e->ev_b);
   e->h_qpos = (uint32_t)qmax;
   // touched flags were summed: any non-zero means touched (getters test != 0)
   return NGSQ_OK;

@@ -77,16 +77,23 @@ __device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
 //   phase B  warp <-> record, 32 times: the per-base work (GC window, quality-by-position), all
 //            lanes on consecutive bytes of one record.
 // General / record counters are summed with one ballot + popcount per counter per 32 records.
-constexpr uint32_t kQualStride = 95;   // 94 scores + 1: odd stride, lanes on consecutive positions hit distinct banks
+// Quality table in shared memory: row stride 95 words (== -1 mod 32) and rows permuted as
+// row(pos) = (pos >> 2) + (pos & 3) * qplane: a lane takes four consecutive positions (one 32-bit
+// load), and for each of its four bytes the 32 lanes of a warp fall into 32 different banks
+// whenever their scores are equal (the common case: a few distinct Phred values per read).
+constexpr uint32_t kQualStride = 95;
+__host__ __device__ inline uint32_t qual_plane(uint32_t qpos_smem) { return (qpos_smem + 3) / 4; }
+__host__ __device__ inline uint32_t qual_rows(uint32_t qpos_smem) { return 4 * qual_plane(qpos_smem); }
 constexpr uint32_t kShortCigar = 8;    // CIGARs up to this many ops are tallied by the record's own lane
 
 __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
   extern __shared__ uint32_t sm[];
   uint32_t* s_qual = sm;
-  uint32_t* s_tlen = s_qual + P.qpos_smem * kQualStride;
+  const uint32_t qplane = qual_plane(P.qpos_smem);
+  uint32_t* s_tlen = s_qual + qual_rows(P.qpos_smem) * kQualStride;
   uint32_t* s_gc = s_tlen + kTlenPad;
   uint32_t* s_cig = s_gc + kGcPad;
-  const uint32_t n_sm = P.qpos_smem * kQualStride + kTlenPad + kGcPad + kCigWords;
+  const uint32_t n_sm = qual_rows(P.qpos_smem) * kQualStride + kTlenPad + kGcPad + kCigWords;
   for (uint32_t i = threadIdx.x; i < n_sm; i += blockDim.x) sm[i] = 0;
   __syncthreads();
 
@@ -243,18 +250,21 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
       const uint32_t ls = __shfl_sync(0xFFFFFFFFu, lseq, j);
       const uint8_t* ql = sq + (ls + 1) / 2;
       const uint32_t gj = __shfl_sync(0xFFFFFFFFu, gc_on ? gc_off : 0xFFFFFFFFu, j);
-      // ---- GC window (gc_content.rs:76-100): 100 bases from the record's offset
+      // ---- GC window (gc_content.rs:76-100): 100 bases from the record's offset, four per lane
       if (gj != 0xFFFFFFFFu) {
         uint32_t gc = 0, at = 0;
+        if (lane < 25) {
+          const uint32_t k0 = gj + 4 * lane;
+          const uint8_t* bp = sq + (k0 >> 1);
+          // three bytes hold the four bases at either nibble phase (the third may lie just past the
+          // window: still inside the record, the qualities follow the sequence)
+          const uint32_t v = ((uint32_t)__ldg(bp) << 16) | ((uint32_t)__ldg(bp + 1) << 8) | (uint32_t)__ldg(bp + 2);
+          const uint32_t u = (v >> ((k0 & 1) ? 4 : 8)) & 0xFFFFu;  // first base in the top nibble
 #pragma unroll
-        for (uint32_t it = 0; it < 4; ++it) {
-          const uint32_t i = it * 32 + lane;
-          if (i < 100) {
-            const uint32_t k = gj + i;
-            const uint32_t byte = __ldg(sq + (k >> 1));
-            const uint32_t code = (k & 1) ? (byte & 15) : (byte >> 4);
-            gc += (code == 2) | (code == 4);
-            at += (code == 1) | (code == 8);
+          for (int jn = 0; jn < 4; ++jn) {
+            const uint32_t code = (u >> (12 - 4 * jn)) & 15u;
+            gc += (0x0014u >> code) & 1u;  // C = 2, G = 4
+            at += (0x0102u >> code) & 1u;  // A = 1, T = 8
           }
         }
         gc = __reduce_add_sync(0xFFFFFFFFu, gc);
@@ -266,11 +276,26 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
       // Qualities are present unless every byte is 0xFF; a present string must be <= 93 throughout,
       // so increments for bytes <= 93 are exact whenever the run does not fail.
       bool any_real = false, any_big = false;
-      for (uint32_t i = lane; i < ls; i += 32) {
+      const uint32_t n_s = ls < P.qpos_smem ? ls : P.qpos_smem;
+      for (uint32_t base = 4 * lane; base < n_s; base += 128) {
+        // four positions per lane from one unaligned 32-bit load (up to 3 bytes past the string: aux data / padding)
+        const uint32_t* wq = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(ql + base) & ~uintptr_t(3));
+        const uint32_t w = __funnelshift_r(__ldg(wq), __ldg(wq + 1), (uint32_t)(reinterpret_cast<uintptr_t>(ql + base) & 3) * 8);
+        uint32_t* row = s_qual + (base >> 2) * kQualStride;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+          const uint32_t q = (w >> (8 * k)) & 255u;
+          if (base + k < n_s) {
+            any_real |= q != 0xFF;
+            if (q > 93) any_big = true;
+            else atomicAdd(row + k * qplane * kQualStride + q, 1u);
+          }
+        }
+      }
+      for (uint32_t i = P.qpos_smem + lane; i < ls; i += 32) {  // long reads: the rest goes to the L2-resident global table
         const uint32_t q = __ldg(ql + i);
         any_real |= q != 0xFF;
         if (q > 93) any_big = true;
-        else if (i < P.qpos_smem) atomicAdd(&s_qual[i * kQualStride + q], 1u);
         else if (i < P.qpos_cap) atomicAdd((unsigned long long*)&P.qual[(uint64_t)i * 94 + q], 1ull);
         else err_rec = 1;
       }
@@ -300,9 +325,10 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
       if (sum_at) atomicAdd((unsigned long long*)&P.res[R_GC_NUC + 1], (unsigned long long)sum_at);
       if (sum_oth) atomicAdd((unsigned long long*)&P.res[R_GC_NUC + 2], (unsigned long long)sum_oth);
     }
-    for (uint32_t i = threadIdx.x; i < P.qpos_smem * kQualStride; i += blockDim.x) {
+    for (uint32_t i = threadIdx.x; i < qual_rows(P.qpos_smem) * kQualStride; i += blockDim.x) {
       const uint32_t v = s_qual[i];
-      const uint32_t qp = i / kQualStride, qs = i - qp * kQualStride;
+      const uint32_t row = i / kQualStride, qs = i - row * kQualStride;
+      const uint32_t qp = (row % qplane) * 4 + row / qplane;  // inverse of the row permutation
       if (v && qs < 94) atomicAdd((unsigned long long*)&P.qual[(uint64_t)qp * 94 + qs], (unsigned long long)v);
     }
     for (uint32_t i = threadIdx.x; i < 1025; i += blockDim.x)

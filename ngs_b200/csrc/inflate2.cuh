@@ -47,6 +47,7 @@ inflate_decode_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
 #pragma unroll 1
       for (int it = 0; it < kDecBatch; ++it) {
         if (L.state == LS_DECODE) L.step();
+        L.settle();  // the input load of this iteration's window slide, consumed only here
         if (!__any_sync(0xFFFFFFFFu, L.state == LS_DECODE)) break;
       }
       if (L.state == LS_DECODE && L.overran()) L.end_block(kBlkBadStream);

@@ -91,15 +91,19 @@ struct InflateCounters {  // host model only
 };
 
 struct Lane {
-  // bit reader: 64-bit buffer (LSB first) fed from two 16-byte register buffers used in turn; the
-  // exhausted one is reloaded in place (no register copies that would wait for the load) and is not
-  // read again before the other one is used up: an input miss has 16 bytes of symbols to hide behind
+  // bit reader: a 128-bit window {w0..w3} of the stream plus the next 64 bits {s0, s1} already
+  // loaded; `pos` (< 64 after refill()) is the bit offset of the next unread bit in the window.
+  // refill() slides the window by 64 bits when pos has passed 64 (the load it issues then is not
+  // consumed before the next slide, >= 64 bits of symbols later) and snapshots the 64 bits at pos
+  // into bb: one refill per symbol covers the worst case (48 bits: length + distance codes and
+  // their extra bits).  ncu drove this shape: a word-at-a-time refill with two call sites cost a
+  // quarter of the kernel's instructions.
   uint64_t bb;
-  int bc;
-  Quad buf_a, buf_b;
-  uint32_t ph;              // 0: reading buf_a, 1: reading buf_b
-  uint32_t n_left;          // words left in the buffer being read
-  const uint8_t *pa, *pb;   // next 16-byte chunk buf_a / buf_b will load (they alternate)
+  uint32_t w0, w1, w2, w3, s0, s1;
+  uint32_t t0, t1;          // target of the load in flight; becomes {s0, s1} in settle()
+  uint32_t shifted;         // a load into {t0, t1} has been issued and not settled yet
+  uint32_t pos;
+  const uint8_t* ptr;       // next 8 bytes to load (window base + 24)
   const uint8_t* in_end;
   // output, in "aligned coordinates": q = block-relative position + (address of the block & 15)
   uint8_t* obase;           // 16-byte aligned address of coordinate 0
@@ -124,63 +128,64 @@ struct Lane {
   NGSQ_HD int16_t* d_base() const { return reinterpret_cast<int16_t*>(slab + SL_DB); }
 
   // ---------------- bit reader ----------------
-  NGSQ_HD uint32_t pop_word() {
-    // the buffers are only ever written by the loads below (selects here, no shifting), so that the
-    // register allocator can keep each one in the aligned register quad the 128-bit load writes
-    const uint32_t wa = n_left == 4 ? buf_a.x : n_left == 3 ? buf_a.y : n_left == 2 ? buf_a.z : buf_a.w;
-    const uint32_t wb = n_left == 4 ? buf_b.x : n_left == 3 ? buf_b.y : n_left == 2 ? buf_b.z : buf_b.w;
-    const uint32_t w = ph ? wb : wa;
-    if (--n_left == 0) {
+  static NGSQ_HD void ld64(const uint8_t* p, uint32_t& lo, uint32_t& hi) {  // p is 8-byte aligned
 #if defined(__CUDA_ARCH__)
-      // Predicated loads straight into the exhausted buffer's registers, each through its own
-      // pointer.  Written as C++ (or with one shared pointer) ptxas merges the two loads into one
-      // load to a temporary followed by moves that wait for it: ncu showed 25 % of all stall
-      // samples of the kernel on those moves.
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %8, 0;\n\t"
-          "@p ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%9];\n\t"
-          "@!p ld.global.nc.v4.u32 {%4,%5,%6,%7}, [%10];\n\t}"
-          : "+r"(buf_b.x), "+r"(buf_b.y), "+r"(buf_b.z), "+r"(buf_b.w), "+r"(buf_a.x), "+r"(buf_a.y), "+r"(buf_a.z), "+r"(buf_a.w)
-          : "r"(ph), "l"(pb), "l"(pa));
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    lo = v.x;
+    hi = v.y;
 #else
-      if (ph) buf_b = ld_in128(pb); else buf_a = ld_in128(pa);
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
 #endif
-      if (ph) pb += 32; else pa += 32;
-      ph ^= 1u;
-      n_left = 4;
-    }
-    return w;
+  }
+  static NGSQ_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // bits [sh, sh+32) of hi:lo, sh < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
   }
   NGSQ_HD void br_init(const uint8_t* p) {
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15);
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 7);
     const uint8_t* base = p - mis;
-    buf_a = ld_in128(base);
-    buf_b = ld_in128(base + 16);
-    pa = base + 32;
-    pb = base + 48;
-    ph = 0;
-    n_left = 4;
-    for (uint32_t k = 0; k < (mis >> 2); ++k) pop_word();
-    const uint32_t w = pop_word();
-    bb = (uint64_t)(w >> (8 * (mis & 3)));
-    bc = 32 - 8 * (int)(mis & 3);
+    ld64(base, w0, w1);
+    ld64(base + 8, w2, w3);
+    ld64(base + 16, s0, s1);
+    ptr = base + 24;
+    pos = 8 * mis;
+    shifted = 0;
     refill();
   }
-  NGSQ_HD void refill() {
-    if (bc <= 32) {
-      bb |= (uint64_t)pop_word() << bc;
-      bc += 32;
-    }
+  // The load issued by a slide goes to {t0, t1} and is copied to {s0, s1} by settle(), which the
+  // symbol loop calls at the END of the iteration (a different basic block, a few hundred
+  // instructions later).  Loading straight into {s0, s1} makes ptxas hoist the load above the
+  // reads of s0/s1, park it in temporaries and copy them at once — a copy that waits for the load.
+  NGSQ_HD void settle() {
+    if (shifted) { s0 = t0; s1 = t1; shifted = 0; }
   }
+  NGSQ_HD void refill() {
+    if (pos >= 64) {
+      w0 = w2; w1 = w3; w2 = s0; w3 = s1;
+      ld64(ptr, t0, t1);
+      ptr += 8;
+      pos -= 64;
+      shifted = 1;
+    }
+    const bool up = pos & 32;
+    const uint32_t a = up ? w1 : w0, b = up ? w2 : w1, c = up ? w3 : w2;
+    const uint32_t sh = pos & 31;
+    bb = (uint64_t)funnel_r(a, b, sh) | ((uint64_t)funnel_r(b, c, sh) << 32);
+  }
+  NGSQ_HD void refill_cold() { refill(); settle(); }  // headers: latency does not matter
   NGSQ_HD uint32_t peek() const { return (uint32_t)bb; }
-  NGSQ_HD void drop(int n) { bb >>= n; bc -= n; }
-  NGSQ_HD uint32_t take(int n) {
+  NGSQ_HD void drop(uint32_t n) { bb >>= n; pos += n; }
+  NGSQ_HD uint32_t take(uint32_t n) {
     uint32_t v = (uint32_t)bb & ((1u << n) - 1u);
     drop(n);
     return v;
   }
   // address of the next unread byte once the reader is byte-aligned
-  NGSQ_HD const uint8_t* byte_ptr() const { return (ph ? pb : pa) - 16 - 4 * n_left - (bc >> 3); }
+  NGSQ_HD const uint8_t* byte_ptr() const { return ptr - 24 + (pos >> 3); }
   // a malformed stream must not run away over the input: a valid one never reads past in_end
   NGSQ_HD bool overran() const { return byte_ptr() > in_end + 8; }
 
@@ -326,15 +331,28 @@ struct Lane {
   // code length of the next symbol: 1 + number of limits the next 15 bits (MSB first) reach
   static NGSQ_HD uint32_t code_len(uint32_t x, const uint32_t* lim_packed) {
     const uint32_t x2 = (x * 0x10001u) | 0x80008000u;
+#if defined(__CUDA_ARCH__)
+    // bit 15 of each half of (x2 - lim) says x >= lim: gather the 16 flag bytes with four byte
+    // permutes, interleave their top bits into one word, popcount
+    const uint32_t g0 = __byte_perm(x2 - lim_packed[0], x2 - lim_packed[1], 0x7531);
+    const uint32_t g1 = __byte_perm(x2 - lim_packed[2], x2 - lim_packed[3], 0x7531);
+    const uint32_t g2 = __byte_perm(x2 - lim_packed[4], x2 - lim_packed[5], 0x7531);
+    const uint32_t g3 = __byte_perm(x2 - lim_packed[6], x2 - lim_packed[7], 0x7531);
+    uint32_t r = g3 & 0x80808080u;
+    r = (g2 & 0x80808080u) | (r >> 1);
+    r = (g1 & 0x80808080u) | (r >> 1);
+    r = (g0 & 0x80808080u) | (r >> 1);
+    return __popc(r) + 1;
+#else
     uint32_t s = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += ((x2 - lim_packed[i]) >> 15) & 0x10001u;  // bit 15 of each half: x >= lim
+    for (int i = 0; i < 8; ++i) s += ((x2 - lim_packed[i]) >> 15) & 0x10001u;
     return (s & 0xFFFFu) + (s >> 16) + 1;
+#endif
   }
 
   // ---------------- DEFLATE block header (+ stored blocks) ----------------
   NGSQ_HD void header() {
-    refill();
+    refill_cold();
     uint32_t h = take(3);
     bfinal = h & 1;
     uint32_t btype = h >> 1;
@@ -346,10 +364,10 @@ struct Lane {
 #ifdef NGSQ_HOST_MODEL
       if (ctr) ctr->stored++;
 #endif
-      drop(bc & 7);
-      refill();
+      drop((0u - pos) & 7u);  // to the next byte boundary
+      refill_cold();
       uint32_t v = take(16);
-      refill();
+      refill_cold();
       uint32_t nv = take(16);
       if ((v ^ nv) != 0xFFFFu) { end_block(kBlkBadStream); return; }
       const uint8_t* sp = byte_ptr();
@@ -368,14 +386,14 @@ struct Lane {
       ok = build([](uint32_t k) -> uint32_t { return k < 144 ? 8u : k < 256 ? 9u : k < 280 ? 7u : 8u; }, 288, ll_sorted(), llim, ll_bt(), nullptr, 256, scratch);
       ok = ok && build([](uint32_t) -> uint32_t { return 5u; }, 32, d_sorted(), dlim, nullptr, d_base(), 0, scratch);
     } else {
-      refill();
+      refill_cold();
       uint32_t v = take(14);
       const uint32_t hlit = (v & 31) + 257, hdist = ((v >> 5) & 31) + 1, hclen = ((v >> 10) & 15) + 4;
       if (hlit > 286 || hdist > 30) { end_block(kBlkBadStream); return; }
       // 19 code-length-code lengths, 3 bits each, kept in one register
       uint64_t clpack = 0;
       for (uint32_t i = 0; i < hclen; ++i) {
-        refill();
+        refill_cold();
         // order: 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
         const uint64_t order = 0xF1E2D3C4B5A69780ull;  // nibbles for i = 3..18
         uint32_t sym = i < 3 ? 16 + i : (uint32_t)((order >> (4 * (i - 3))) & 15);
@@ -421,12 +439,12 @@ struct Lane {
       uint32_t i = 0, word = 0, prevlen = 0;
       bool bad = false;
       while (i < total) {
-        refill();
+        refill_cold();
         if (overran()) { bad = true; break; }
         uint32_t e = cl_lut[peek() & 127];
         uint32_t l = e & 7, sym = e >> 3;
         if (!l) { bad = true; break; }
-        drop((int)l);
+        drop(l);
         uint32_t rep = 1, val = sym;
         if (sym == 16) { if (i == 0) { bad = true; break; } val = prevlen; rep = 3 + take(2); }
         else if (sym == 17) { val = 0; rep = 3 + take(3); }
@@ -460,7 +478,7 @@ struct Lane {
     const uint32_t idx = ((x >> (15 - len)) + bt) & 0xFFFFu;  // index into sorted (the base is kept mod 2^16)
     const uint32_t s8 = ll_sorted()[idx < 288 ? idx : 0];
     const bool upper = idx >= (bt >> 16);  // symbol >= 256
-    drop((int)len);
+    drop(len);
 #ifdef NGSQ_HOST_MODEL
     if (ctr) { ctr->symbols++; ctr->ll_len_hist[len]++; }
 #endif
@@ -478,16 +496,15 @@ struct Lane {
       else if (li == 28) mlen = 258;
       else {
         const uint32_t eb = (li - 4) >> 2;
-        mlen = 3 + ((4 + (li & 3)) << eb) + take((int)eb);
+        mlen = 3 + ((4 + (li & 3)) << eb) + take(eb);
       }
-      refill();
       const uint32_t dx = brev32(peek()) >> 17;
       const uint32_t dl = code_len(dx, dlim);
       if (dl > 15) { end_block(kBlkBadStream); return; }
       const uint32_t di = ((dx >> (15 - dl)) + (uint32_t)(int)d_base()[dl]) & 31u;
       const uint32_t ds = d_sorted()[di];
       if (ds > 29) { end_block(kBlkBadStream); return; }
-      drop((int)dl);
+      drop(dl);
 #ifdef NGSQ_HOST_MODEL
       if (ctr) ctr->d_len_hist[dl]++;
 #endif
@@ -495,7 +512,7 @@ struct Lane {
       if (ds < 4) dist = 1 + ds;
       else {
         const uint32_t deb = (ds >> 1) - 1;
-        dist = 1 + ((2 + (ds & 1)) << deb) + take((int)deb);
+        dist = 1 + ((2 + (ds & 1)) << deb) + take(deb);
       }
       const uint32_t p = q - q0;
       if (dist > p || q + mlen > qend) { end_block(kBlkOverrun); return; }

@@ -66,6 +66,7 @@ int main(int argc, char** argv) {
           if (L.state == LS_HEADER) L.header();
           else {
             L.step();
+            L.settle();
             if (L.state == LS_DECODE && L.overran()) L.end_block(kBlkBadStream);
           }
         }
