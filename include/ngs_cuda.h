@@ -126,7 +126,7 @@ int ngsq_bgzf_walk(const uint8_t* bgzf, size_t nbytes, uint64_t file_off, ngsq_b
                    uint32_t* n_blocks, size_t* consumed);
 
 /* Streams one chunk of whole BGZF blocks from HOST memory: async H2D copy; the inflate kernels are
- * launched whenever a whole wave of blocks has been copied (and by ngsq_finish for the rest), so the
+ * launched whenever launch_blocks blocks have been copied (and by ngsq_finish for the rest), so the
  * copy of one chunk overlaps the kernels of the previous ones.  The buffer must stay valid until
  * ngsq_finish returns.  Chunks must be submitted in file order. */
 int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t file_off);

@@ -37,7 +37,7 @@ constexpr uint32_t R_FIXED_WORDS = 1184;
 // per contig slot: [0] touched, [1] pileup_too_large, [2..2051) depth histogram, [2051..) bin sums
 constexpr uint32_t COV_TOUCHED = 0, COV_TOO_LARGE = 1, COV_HIST = 2, COV_BINS = 2051;
 
-constexpr int kFacetThreads = 512;
+constexpr int kFacetThreads = 224;  // 7 warps, each with a private 15 KB quality table: two CTAs per SM
 constexpr uint32_t kTlenPad = 1028, kGcPad = 104, kCigWords = 18 * 32;
 
 struct FacetParams {
@@ -77,23 +77,71 @@ __device__ __forceinline__ uint64_t splitmix64_dev(uint64_t x) {
 //   phase B  warp <-> record, 32 times: the per-base work (GC window, quality-by-position), all
 //            lanes on consecutive bytes of one record.
 // General / record counters are summed with one ballot + popcount per counter per 32 records.
-// Quality table in shared memory: row stride 95 words (== -1 mod 32) and rows permuted as
-// row(pos) = (pos >> 2) + (pos & 3) * qplane: a lane takes four consecutive positions (one 32-bit
-// load), and for each of its four bytes the 32 lanes of a warp fall into 32 different banks
-// whenever their scores are equal (the common case: a few distinct Phred values per read).
-constexpr uint32_t kQualStride = 95;
-__host__ __device__ inline uint32_t qual_plane(uint32_t qpos_smem) { return (qpos_smem + 3) / 4; }
-__host__ __device__ inline uint32_t qual_rows(uint32_t qpos_smem) { return 4 * qual_plane(qpos_smem); }
+// Quality-by-position in shared memory.  Shared-memory ATOMICS run at about one lane per clock per
+// SM (ncu, profiles/: the CTA-shared u32 table made this kernel atomics-bound, 150 per record), so
+// every WARP owns a private table of 8-bit counters and updates it with plain load/add/store: the
+// lanes of a warp hold different positions of one record (distinct bytes), and no other warp
+// touches the table.  A counter grows by at most one per record, so the warp adds its table into
+// the global u64 table every kQualFlushRecords (< 256) records.  Row stride 100 bytes = 25 words
+// (odd): lanes on consecutive positions with equal scores fall into different banks.
+constexpr uint32_t kQualRowBytes = 100;
+constexpr uint32_t kQualFlushSteps = 7;  // x 32 records per warp step = 224 < 256
+__host__ __device__ inline uint32_t qual_table_bytes(uint32_t qpos_smem) { return (qpos_smem * kQualRowBytes + 15u) & ~15u; }
+
 constexpr uint32_t kShortCigar = 8;    // CIGARs up to this many ops are tallied by the record's own lane
+
+// adds a warp's private 8-bit table into the global table and clears it
+__device__ __forceinline__ void flush_qual_table(uint32_t* tab_words, uint32_t n_words, unsigned long long* gqual, uint32_t lane) {
+  for (uint32_t wi = lane; wi < n_words; wi += 32) {
+    const uint32_t v = tab_words[wi];
+    if (v) {
+      tab_words[wi] = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 4; ++k) {
+        const uint32_t c = (v >> (8 * k)) & 255u;
+        if (c) {
+          const uint32_t byte = wi * 4 + k, qp = byte / kQualRowBytes, qs = byte - qp * kQualRowBytes;
+          atomicAdd(&gqual[(uint64_t)qp * 94 + qs], (unsigned long long)c);
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+constexpr uint32_t kQualPre = 5;  // quality positions per lane loaded one record ahead (covers reads up to 160 bases)
+
+// loads of one record that phase B needs: quality bytes at positions lane + 32k (0x100 where the
+// string or the shared-memory table ends) and, for lanes < 25 of a GC-eligible record, the three
+// sequence bytes holding bases gj + 4*lane .. +3 at either nibble phase (the third byte may lie just
+// past the window: still inside the record, the qualities follow the sequence)
+__device__ __forceinline__ void facet_prefetch(const uint8_t* sq, uint32_t ls, uint32_t gj, uint32_t qpos_smem, uint32_t lane,
+                                               uint32_t (&qb)[kQualPre], uint32_t& gb) {
+  const uint8_t* ql = sq + (ls + 1) / 2;
+  const uint32_t n_s = ls < qpos_smem ? ls : qpos_smem;
+#pragma unroll
+  for (uint32_t k = 0; k < kQualPre; ++k) {
+    const uint32_t i = lane + 32 * k;
+    qb[k] = i < n_s ? (uint32_t)__ldg(ql + i) : 0x100u;
+  }
+  gb = 0;
+  if (gj != 0xFFFFFFFFu && lane < 25) {
+    const uint8_t* bp = sq + ((gj + 4 * lane) >> 1);
+    gb = ((uint32_t)__ldg(bp) << 16) | ((uint32_t)__ldg(bp + 1) << 8) | (uint32_t)__ldg(bp + 2);
+  }
+}
 
 __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
   extern __shared__ uint32_t sm[];
-  uint32_t* s_qual = sm;
-  const uint32_t qplane = qual_plane(P.qpos_smem);
-  uint32_t* s_tlen = s_qual + qual_rows(P.qpos_smem) * kQualStride;
+  const uint32_t warps_in_cta = blockDim.x >> 5;
+  const uint32_t qtab_words = qual_table_bytes(P.qpos_smem) / 4;
+  uint32_t* s_tlen = sm + qtab_words * warps_in_cta;
   uint32_t* s_gc = s_tlen + kTlenPad;
   uint32_t* s_cig = s_gc + kGcPad;
-  const uint32_t n_sm = qual_rows(P.qpos_smem) * kQualStride + kTlenPad + kGcPad + kCigWords;
+  const uint32_t n_sm = qtab_words * warps_in_cta + kTlenPad + kGcPad + kCigWords;
+  uint32_t* my_qwords = sm + qtab_words * (threadIdx.x >> 5);          // this warp's private table
+  uint8_t* my_qtab = reinterpret_cast<uint8_t*>(my_qwords);
+  uint32_t steps_since_flush = 0;
   for (uint32_t i = threadIdx.x; i < n_sm; i += blockDim.x) sm[i] = 0;
   __syncthreads();
 
@@ -244,25 +292,39 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
     }
 
     // ================= phase B: one record per warp step =================
-    for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, rec_on && lseq != 0); todo; todo &= todo - 1) {
-      const int j = __ffs(todo) - 1;
-      const uint8_t* sq = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)seq, j));
-      const uint32_t ls = __shfl_sync(0xFFFFFFFFu, lseq, j);
+    // Software-pipelined: the bytes of the NEXT record (first 160 quality positions, the three
+    // sequence bytes of this lane's part of the GC window) are loaded before the current record is
+    // tallied, so a warp always has one record's worth of loads in flight.
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, rec_on && lseq != 0);
+    const uint8_t* sq = nullptr;   // current record
+    uint32_t ls = 0, gj = 0xFFFFFFFFu;
+    uint32_t qb[kQualPre], gb = 0;  // prefetched: quality bytes (0x100 = beyond the string), packed GC bytes
+    {
+      const int j = todo ? __ffs(todo) - 1 : 0;
+      sq = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)seq, j));
+      ls = __shfl_sync(0xFFFFFFFFu, lseq, j);
+      gj = __shfl_sync(0xFFFFFFFFu, gc_on ? gc_off : 0xFFFFFFFFu, j);
+      if (todo) facet_prefetch(sq, ls, gj, P.qpos_smem, lane, qb, gb);
+    }
+    while (todo) {
+      todo &= todo - 1;
+      // ---- issue the next record's loads
+      const int jn = todo ? __ffs(todo) - 1 : 0;
+      const uint8_t* sq_n = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)seq, jn));
+      const uint32_t ls_n = __shfl_sync(0xFFFFFFFFu, lseq, jn);
+      const uint32_t gj_n = __shfl_sync(0xFFFFFFFFu, gc_on ? gc_off : 0xFFFFFFFFu, jn);
+      uint32_t qb_n[kQualPre], gb_n = 0;
+      if (todo) facet_prefetch(sq_n, ls_n, gj_n, P.qpos_smem, lane, qb_n, gb_n);
       const uint8_t* ql = sq + (ls + 1) / 2;
-      const uint32_t gj = __shfl_sync(0xFFFFFFFFu, gc_on ? gc_off : 0xFFFFFFFFu, j);
       // ---- GC window (gc_content.rs:76-100): 100 bases from the record's offset, four per lane
       if (gj != 0xFFFFFFFFu) {
         uint32_t gc = 0, at = 0;
         if (lane < 25) {
           const uint32_t k0 = gj + 4 * lane;
-          const uint8_t* bp = sq + (k0 >> 1);
-          // three bytes hold the four bases at either nibble phase (the third may lie just past the
-          // window: still inside the record, the qualities follow the sequence)
-          const uint32_t v = ((uint32_t)__ldg(bp) << 16) | ((uint32_t)__ldg(bp + 1) << 8) | (uint32_t)__ldg(bp + 2);
-          const uint32_t u = (v >> ((k0 & 1) ? 4 : 8)) & 0xFFFFu;  // first base in the top nibble
+          const uint32_t u = (gb >> ((k0 & 1) ? 4 : 8)) & 0xFFFFu;  // first base in the top nibble
 #pragma unroll
-          for (int jn = 0; jn < 4; ++jn) {
-            const uint32_t code = (u >> (12 - 4 * jn)) & 15u;
+          for (int jb = 0; jb < 4; ++jb) {
+            const uint32_t code = (u >> (12 - 4 * jb)) & 15u;
             gc += (0x0014u >> code) & 1u;  // C = 2, G = 4
             at += (0x0102u >> code) & 1u;  // A = 1, T = 8
           }
@@ -276,20 +338,26 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
       // Qualities are present unless every byte is 0xFF; a present string must be <= 93 throughout,
       // so increments for bytes <= 93 are exact whenever the run does not fail.
       bool any_real = false, any_big = false;
-      const uint32_t n_s = ls < P.qpos_smem ? ls : P.qpos_smem;
-      for (uint32_t base = 4 * lane; base < n_s; base += 128) {
-        // four positions per lane from one unaligned 32-bit load (up to 3 bytes past the string: aux data / padding)
-        const uint32_t* wq = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(ql + base) & ~uintptr_t(3));
-        const uint32_t w = __funnelshift_r(__ldg(wq), __ldg(wq + 1), (uint32_t)(reinterpret_cast<uintptr_t>(ql + base) & 3) * 8);
-        uint32_t* row = s_qual + (base >> 2) * kQualStride;
 #pragma unroll
-        for (uint32_t k = 0; k < 4; ++k) {
-          const uint32_t q = (w >> (8 * k)) & 255u;
-          if (base + k < n_s) {
-            any_real |= q != 0xFF;
-            if (q > 93) any_big = true;
-            else atomicAdd(row + k * qplane * kQualStride + q, 1u);
+      for (uint32_t k = 0; k < kQualPre; ++k) {
+        const uint32_t q = qb[k];
+        if (q <= 0xFF) {
+          any_real |= q != 0xFF;
+          if (q > 93) any_big = true;
+          else {
+            uint8_t* c = my_qtab + (lane + 32 * k) * kQualRowBytes + q;  // private to this warp; lanes hold distinct positions
+            *c = (uint8_t)(*c + 1);
           }
+        }
+      }
+      const uint32_t n_s = ls < P.qpos_smem ? ls : P.qpos_smem;
+      for (uint32_t i = 32 * kQualPre + lane; i < n_s; i += 32) {  // shared-memory positions beyond the prefetched ones
+        const uint32_t q = __ldg(ql + i);
+        any_real |= q != 0xFF;
+        if (q > 93) any_big = true;
+        else {
+          uint8_t* c = my_qtab + i * kQualRowBytes + q;
+          *c = (uint8_t)(*c + 1);
         }
       }
       for (uint32_t i = P.qpos_smem + lane; i < ls; i += 32) {  // long reads: the rest goes to the L2-resident global table
@@ -305,8 +373,17 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
         if (any_big) err_qual = 1;
         max_qpos = ls > max_qpos ? ls : max_qpos;
       }
+      sq = sq_n; ls = ls_n; gj = gj_n; gb = gb_n;
+#pragma unroll
+      for (uint32_t k = 0; k < kQualPre; ++k) qb[k] = qb_n[k];
+    }
+    __syncwarp();
+    if (++steps_since_flush == kQualFlushSteps) {
+      flush_qual_table(my_qwords, qtab_words, (unsigned long long*)P.qual, lane);
+      steps_since_flush = 0;
     }
   }
+  if (do_rec && steps_since_flush) flush_qual_table(my_qwords, qtab_words, (unsigned long long*)P.qual, lane);
 
   // ---- flush ----
   __syncthreads();
@@ -324,12 +401,6 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
       if (sum_gc) atomicAdd((unsigned long long*)&P.res[R_GC_NUC + 0], (unsigned long long)sum_gc);
       if (sum_at) atomicAdd((unsigned long long*)&P.res[R_GC_NUC + 1], (unsigned long long)sum_at);
       if (sum_oth) atomicAdd((unsigned long long*)&P.res[R_GC_NUC + 2], (unsigned long long)sum_oth);
-    }
-    for (uint32_t i = threadIdx.x; i < qual_rows(P.qpos_smem) * kQualStride; i += blockDim.x) {
-      const uint32_t v = s_qual[i];
-      const uint32_t row = i / kQualStride, qs = i - row * kQualStride;
-      const uint32_t qp = (row % qplane) * 4 + row / qplane;  // inverse of the row permutation
-      if (v && qs < 94) atomicAdd((unsigned long long*)&P.qual[(uint64_t)qp * 94 + qs], (unsigned long long)v);
     }
     for (uint32_t i = threadIdx.x; i < 1025; i += blockDim.x)
       if (s_tlen[i]) atomicAdd((unsigned long long*)&P.res[R_TLEN_HIST + i], (unsigned long long)s_tlen[i]);
