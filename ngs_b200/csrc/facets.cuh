@@ -90,18 +90,19 @@ __host__ __device__ inline uint32_t qual_table_bytes(uint32_t qpos_smem) { retur
 
 constexpr uint32_t kShortCigar = 8;    // CIGARs up to this many ops are tallied by the record's own lane
 
-// adds a warp's private 8-bit table into the global table and clears it
-__device__ __forceinline__ void flush_qual_table(uint32_t* tab_words, uint32_t n_words, unsigned long long* gqual, uint32_t lane) {
-  for (uint32_t wi = lane; wi < n_words; wi += 32) {
-    const uint32_t v = tab_words[wi];
-    if (v) {
-      tab_words[wi] = 0;
+// adds a warp's private 8-bit table into the global table and clears it: one row (position) per
+// lane, so that all lanes stay busy (a row holds a handful of non-zero counters)
+__device__ __forceinline__ void flush_qual_table(uint32_t* tab_words, uint32_t n_rows, unsigned long long* gqual, uint32_t lane) {
+  for (uint32_t row = lane; row < n_rows; row += 32) {
+    uint32_t* rw = tab_words + row * (kQualRowBytes / 4);
+    for (uint32_t wi = 0; wi < 94 / 4 + 1; ++wi) {
+      const uint32_t v = rw[wi];
+      if (v) {
+        rw[wi] = 0;
 #pragma unroll
-      for (uint32_t k = 0; k < 4; ++k) {
-        const uint32_t c = (v >> (8 * k)) & 255u;
-        if (c) {
-          const uint32_t byte = wi * 4 + k, qp = byte / kQualRowBytes, qs = byte - qp * kQualRowBytes;
-          atomicAdd(&gqual[(uint64_t)qp * 94 + qs], (unsigned long long)c);
+        for (uint32_t k = 0; k < 4; ++k) {
+          const uint32_t c = (v >> (8 * k)) & 255u;
+          if (c) atomicAdd(&gqual[(uint64_t)row * 94 + wi * 4 + k], (unsigned long long)c);
         }
       }
     }
@@ -116,18 +117,23 @@ constexpr uint32_t kQualPre = 5;  // quality positions per lane loaded one recor
 // sequence bytes holding bases gj + 4*lane .. +3 at either nibble phase (the third byte may lie just
 // past the window: still inside the record, the qualities follow the sequence)
 __device__ __forceinline__ void facet_prefetch(const uint8_t* sq, uint32_t ls, uint32_t gj, uint32_t qpos_smem, uint32_t lane,
-                                               uint32_t (&qb)[kQualPre], uint32_t& gb) {
+                                               uint32_t (&qb)[kQualPre], uint32_t (&gb)[3]) {
+  // nothing here may consume a loaded value (no selects, no shifts): the loads must stay in flight
+  // while the previous record is tallied
   const uint8_t* ql = sq + (ls + 1) / 2;
   const uint32_t n_s = ls < qpos_smem ? ls : qpos_smem;
 #pragma unroll
   for (uint32_t k = 0; k < kQualPre; ++k) {
     const uint32_t i = lane + 32 * k;
-    qb[k] = i < n_s ? (uint32_t)__ldg(ql + i) : 0x100u;
+    qb[k] = 0x100u;
+    if (i < n_s) qb[k] = __ldg(ql + i);
   }
-  gb = 0;
+  gb[0] = gb[1] = gb[2] = 0;
   if (gj != 0xFFFFFFFFu && lane < 25) {
     const uint8_t* bp = sq + ((gj + 4 * lane) >> 1);
-    gb = ((uint32_t)__ldg(bp) << 16) | ((uint32_t)__ldg(bp + 1) << 8) | (uint32_t)__ldg(bp + 2);
+    gb[0] = __ldg(bp);
+    gb[1] = __ldg(bp + 1);
+    gb[2] = __ldg(bp + 2);
   }
 }
 
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
     uint32_t todo = __ballot_sync(0xFFFFFFFFu, rec_on && lseq != 0);
     const uint8_t* sq = nullptr;   // current record
     uint32_t ls = 0, gj = 0xFFFFFFFFu;
-    uint32_t qb[kQualPre], gb = 0;  // prefetched: quality bytes (0x100 = beyond the string), packed GC bytes
+    uint32_t qb[kQualPre], gb[3];  // prefetched: quality bytes (0x100 = beyond the string), GC window bytes
     {
       const int j = todo ? __ffs(todo) - 1 : 0;
       sq = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)seq, j));
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
       const uint8_t* sq_n = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)seq, jn));
       const uint32_t ls_n = __shfl_sync(0xFFFFFFFFu, lseq, jn);
       const uint32_t gj_n = __shfl_sync(0xFFFFFFFFu, gc_on ? gc_off : 0xFFFFFFFFu, jn);
-      uint32_t qb_n[kQualPre], gb_n = 0;
+      uint32_t qb_n[kQualPre], gb_n[3];
       if (todo) facet_prefetch(sq_n, ls_n, gj_n, P.qpos_smem, lane, qb_n, gb_n);
       const uint8_t* ql = sq + (ls + 1) / 2;
       // ---- GC window (gc_content.rs:76-100): 100 bases from the record's offset, four per lane
@@ -321,7 +327,8 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
         uint32_t gc = 0, at = 0;
         if (lane < 25) {
           const uint32_t k0 = gj + 4 * lane;
-          const uint32_t u = (gb >> ((k0 & 1) ? 4 : 8)) & 0xFFFFu;  // first base in the top nibble
+          const uint32_t v = (gb[0] << 16) | (gb[1] << 8) | gb[2];
+          const uint32_t u = (v >> ((k0 & 1) ? 4 : 8)) & 0xFFFFu;  // first base in the top nibble
 #pragma unroll
           for (int jb = 0; jb < 4; ++jb) {
             const uint32_t code = (u >> (12 - 4 * jb)) & 15u;
@@ -373,17 +380,17 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
         if (any_big) err_qual = 1;
         max_qpos = ls > max_qpos ? ls : max_qpos;
       }
-      sq = sq_n; ls = ls_n; gj = gj_n; gb = gb_n;
+      sq = sq_n; ls = ls_n; gj = gj_n; gb[0] = gb_n[0]; gb[1] = gb_n[1]; gb[2] = gb_n[2];
 #pragma unroll
       for (uint32_t k = 0; k < kQualPre; ++k) qb[k] = qb_n[k];
     }
     __syncwarp();
     if (++steps_since_flush == kQualFlushSteps) {
-      flush_qual_table(my_qwords, qtab_words, (unsigned long long*)P.qual, lane);
+      flush_qual_table(my_qwords, P.qpos_smem, (unsigned long long*)P.qual, lane);
       steps_since_flush = 0;
     }
   }
-  if (do_rec && steps_since_flush) flush_qual_table(my_qwords, qtab_words, (unsigned long long*)P.qual, lane);
+  if (do_rec && steps_since_flush) flush_qual_table(my_qwords, P.qpos_smem, (unsigned long long*)P.qual, lane);
 
   // ---- flush ----
   __syncthreads();
