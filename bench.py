@@ -331,10 +331,16 @@ def main():
         eng.finish()
         eng.reduce(0)
         if rank == 0:
-            got_m = collect(eng, lens, enabled)
-            wb, wbai, _ = ffi.synth_bam(shape, sn, level=6)
-            assert_same_ints(got_m, oracle_ints(wb, wbai, gc_seed=7))
-            merged_parity = f"{N}-rank shards + NCCL reduce bit-exact vs oracle on the whole {sn}-record sample"
+            try:
+                got_m = collect(eng, lens, enabled)
+                wb, wbai, _ = ffi.synth_bam(shape, sn, level=6)
+                # every rank wrote its own shard file, so records sit at other virtual offsets than in the
+                # whole file and the GC window offsets differ: compare the GC fields that do not depend on it
+                assert_same_ints(got_m, oracle_ints(wb, wbai, gc_seed=7), gc_window=False)
+                merged_parity = (f"{N}-rank shards + NCCL reduce bit-exact vs oracle on the whole {sn}-record sample "
+                                 "(GC window histogram: invariants only, shard files have their own virtual offsets)")
+            except AssertionError as ex:  # never leave the other ranks waiting
+                merged_parity = "FAILED: " + str(ex).strip().splitlines()[-1][:200]
         log("merged parity checked")
     if rank == 0 and not args.no_cpu:
         sn = args.cpu_sample
@@ -398,6 +404,8 @@ def main():
     lib.ngsq_host_free(pin_ptr)
     if N > 1:
         dist.destroy_process_group()
+    if merged_parity and merged_parity.startswith("FAILED"):
+        raise SystemExit("merged parity check failed: " + merged_parity)
 
 
 if __name__ == "__main__":
