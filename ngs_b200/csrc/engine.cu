@@ -364,9 +364,17 @@ int launch_pending(ngsq_engine* e, uint32_t upto) {
 }
 
 uint32_t launch_quantum(const ngsq_engine* e) {
-  // one wave: a launch takes about one block-decode latency whatever its size (every lane decodes its
-  // block serially), so smaller launches only add latencies; measured: half waves made e2e 40 % slower
-  return e->cfg.launch_blocks ? e->cfg.launch_blocks : (uint32_t)e->n_sm * kDecThreads;
+  // One wave: a launch takes about one block-decode latency whatever its size (every lane decodes its
+  // block serially), so smaller launches only add latencies; measured: half waves made e2e 40 % slower.
+  // When the caller announced the number of blocks (reserve_blocks), the waves are made equal so that no
+  // small remainder launch (a full latency for a few blocks) is left for ngsq_finish.
+  if (e->cfg.launch_blocks) return e->cfg.launch_blocks;
+  const uint32_t wave = (uint32_t)e->n_sm * kDecThreads;
+  if (e->cfg.reserve_blocks > wave) {
+    const uint32_t n_waves = (e->cfg.reserve_blocks + wave - 1) / wave;
+    return (e->cfg.reserve_blocks + n_waves - 1) / n_waves;
+  }
+  return wave;
 }
 
 }  // namespace
