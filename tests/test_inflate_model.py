@@ -80,3 +80,20 @@ def test_decoder_matches_zlib_on_synthetic_bam(model, tmp_path):
         r = subprocess.run([model, str(path)], capture_output=True, text=True)
         assert r.returncode == 0, r.stdout + r.stderr
         assert "bad 0" in r.stdout
+
+
+def test_decoder_survives_corrupted_streams(model, tmp_path):
+    """Bit flips in the DEFLATE payload: the decoder must reject the block or finish it, never write
+    outside the block's output range, never mark matches beyond it, never emit an unresolvable token
+    (the resolve kernel trusts tokens of blocks that decoded without error) and never run away."""
+    from ngs_b200 import ffi
+    bam, _, _ = ffi.synth_bam(1, 6000, level=6)
+    out = bam.tobytes()
+    for payload, lvl, strat in [(b"ACGT" * 9000, 6, zlib.Z_FIXED), (bytes(range(256)) * 200, 0, zlib.Z_DEFAULT_STRATEGY),
+                                (b"A" * 65000, 9, zlib.Z_DEFAULT_STRATEGY)]:
+        out += bgzf_block(payload, lvl, strat)
+    path = tmp_path / "fuzz.bgzf"
+    path.write_bytes(out)
+    r = subprocess.run([model, str(path), "--fuzz", "60"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bad 0" in r.stdout

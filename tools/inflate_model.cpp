@@ -4,6 +4,8 @@
 // and prints symbol statistics that drive kernel design decisions.
 //   g++ -O2 -std=c++17 -DNGSQ_HOST_MODEL -o /tmp/inflate_model tools/inflate_model.cpp -lz
 //   /tmp/inflate_model file.bam [max_blocks]
+//   /tmp/inflate_model file.bam --fuzz N     N corrupted copies of every block: the decoder must fail
+//                                            or finish, never write outside its block, never run away
 #include <zlib.h>
 
 #include <cstdio>
@@ -27,6 +29,9 @@ int main(int argc, char** argv) {
   if (fread(buf.data(), 1, n, f) != n) { perror("read"); return 2; }
   fclose(f);
   size_t max_blocks = argc > 2 ? strtoull(argv[2], nullptr, 10) : ~size_t(0);
+  int fuzz = 0;
+  if (argc > 3 && !strcmp(argv[2], "--fuzz")) { fuzz = atoi(argv[3]); max_blocks = ~size_t(0); }
+  uint64_t fuzz_runs = 0, fuzz_failed = 0, fuzz_ok = 0, rng = 0x9E3779B97F4A7C15ull;
 
   InflateCounters ctr;
   std::vector<uint8_t> slab(kSlabBytes);
@@ -48,7 +53,55 @@ int main(int argc, char** argv) {
     memcpy(&crc, h + total - 8, 4);
     uint32_t hdr = 12 + xlen;
     uint32_t clen = (uint32_t)total - hdr - 8;
-    if (isize) {
+    for (int fz = 0; fz < fuzz && isize; ++fz) {
+      // corrupt 1-3 bytes of a private copy of the payload (with the reader's look-ahead padding)
+      std::vector<uint8_t> pay(clen + 1024, 0);
+      memcpy(pay.data(), h + hdr, clen);
+      int nflip = 1 + (int)(rng >> 62) % 3;
+      for (int k = 0; k < nflip; ++k) {
+        rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+        pay[(rng >> 33) % clen] ^= (uint8_t)(1u << ((rng >> 20) & 7));
+      }
+      BlockDesc d;
+      d.in_off = (uint64_t)(uintptr_t)pay.data();
+      d.out_off = 16 + (fz & 3);
+      d.clen = clen;
+      d.isize = isize;
+      memset(out.data(), 0xAA, out.size());
+      memset(bitmap.data(), 0, kBitmapWords * 4);
+      Lane L;
+      L.slab = slab.data();
+      L.ctr = nullptr;
+      L.begin_block(d, out.data(), bitmap.data());
+      uint64_t steps = 0;
+      while (L.state != LS_IDLE && steps < 4000000) {
+        if (L.state == LS_HEADER) L.header();
+        else {
+          L.step();
+          L.settle();
+          if (L.state == LS_DECODE && L.overran()) L.end_block(kBlkBadStream);
+        }
+        ++steps;
+      }
+      if (L.state != LS_IDLE) { fprintf(stderr, "fuzz: block at %zu did not terminate\n", o); bad++; }
+      uint8_t* ob = out.data() + d.out_off;
+      for (int g = 1; g <= 12; ++g)
+        if (ob[-g] != 0xAA || ob[isize + g - 1] != 0xAA) { fprintf(stderr, "fuzz: block at %zu wrote outside its range\n", o); bad++; break; }
+      for (uint32_t w = (isize + 31) / 32 + 1; w < kBitmapWords; ++w)
+        if (bitmap[w]) { fprintf(stderr, "fuzz: block at %zu marked a match beyond its size\n", o); bad++; break; }
+      if (!L.err) {  // decoded "successfully": every token must be resolvable inside the block
+        for (uint32_t w = 0; w < kBitmapWords; ++w)
+          for (uint32_t m = bitmap[w]; m; m &= m - 1) {
+            uint32_t p = w * 32 + __builtin_ctz(m);
+            uint32_t tok = ob[p] | (ob[p + 1] << 8) | (ob[p + 2] << 16);
+            uint32_t mlen = (tok & 255) + 3, dist = (tok >> 8) + 1;
+            if (dist > p || p + mlen > isize) { fprintf(stderr, "fuzz: block at %zu holds an invalid token\n", o); bad++; w = kBitmapWords; break; }
+          }
+        fuzz_ok++;
+      } else fuzz_failed++;
+      fuzz_runs++;
+    }
+    if (isize && !fuzz) {
       for (int mis = 0; mis < 4; mis += 3) {  // two output alignments
         BlockDesc d;
         d.in_off = (uint64_t)(uintptr_t)(h + hdr);
@@ -142,6 +195,11 @@ int main(int argc, char** argv) {
       total_in += clen;
     }
     o += total;
+  }
+  if (fuzz) {
+    printf("fuzz: %llu corrupted blocks, %llu rejected, %llu decoded, bad %llu\n", (unsigned long long)fuzz_runs,
+           (unsigned long long)fuzz_failed, (unsigned long long)fuzz_ok, (unsigned long long)bad);
+    return bad ? 1 : 0;
   }
   printf("blocks %llu, in %llu, out %llu (ratio %.2f), bad %llu\n", (unsigned long long)n_blocks, (unsigned long long)total_in,
          (unsigned long long)total_out, (double)total_out / total_in, (unsigned long long)bad);
