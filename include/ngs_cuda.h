@@ -70,7 +70,7 @@ typedef struct ngsq_config {
   uint64_t reserve_inflated;
   uint32_t reserve_blocks;
   uint32_t launch_blocks;      /* tuning/testing: BGZF blocks per inflate launch of ngsq_submit; 0 = one wave of the
-                                  decode kernel (one block per lane, SMs x 512 lanes) */
+                                  decode kernel (one block per lane, SMs x 544 lanes) */
 } ngsq_config;
 
 /* One BGZF block as framed by the host (K1). */

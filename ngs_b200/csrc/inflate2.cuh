@@ -21,7 +21,7 @@
 namespace ngsq {
 
 constexpr int kDecBatch = 32;  // symbols per lane between header / overrun checks
-constexpr int kDecWarps = (227 * 1024 / kSlabBytes) / 32 > 16 ? 16 : (227 * 1024 / kSlabBytes) / 32;
+constexpr int kDecWarps = (227 * 1024 / kSlabBytes) / 32 > 17 ? 17 : (227 * 1024 / kSlabBytes) / 32;  // 17 x 32 x 420 B of slabs; 120 registers per thread
 constexpr int kDecThreads = kDecWarps * 32;
 constexpr size_t kDecSmem = (size_t)kDecThreads * kSlabBytes;
 
