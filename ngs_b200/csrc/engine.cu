@@ -3,7 +3,8 @@
 //   compressed BGZF bytes | inflated byte stream (contiguous, blocks at ISIZE prefix sums)
 //   | block tables | record offset table (8 B/record) | per-contig int32 difference arrays
 //   | packed u64 result buffer (the NCCL reduce payload).
-// Streams: H2D copies on s_copy, kernels on s_comp; each submitted chunk's inflate launch waits
+// Streams: H2D copies on s_copy, kernels on s_comp, the per-block CRC32 check on s_aux (it depends only on the
+// inflated bytes, so it runs beside the record scan and the facet kernel); each submitted chunk's inflate launch waits
 // only for its own copy, so PCIe transfer of chunk k+1 overlaps inflate of chunk k.
 #include <dlfcn.h>
 
@@ -77,11 +78,11 @@ struct ngsq_engine {
   int n_sm = 0;
   ngsq_config cfg{};
   std::string err;
-  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr;
   std::vector<cudaEvent_t> copy_events;
   std::vector<uint32_t> copy_upto;  // h_blocks.size() once the chunk of copy_events[i] was appended
   uint32_t launched = 0;            // blocks [0, launched) have been handed to the inflate kernels
-  struct InflateEvents { cudaEvent_t begin, decoded_from, decoded, end, crc_end; };
+  struct InflateEvents { cudaEvent_t begin, decoded_from, decoded, end, crc_begin, crc_end; };
   std::vector<InflateEvents> inflate_events;
   cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr, ev_f = nullptr;
   bool run_started = false, finished = false;
@@ -172,6 +173,7 @@ int grow(ngsq_engine* e, T*& ptr, size_t& cap, size_t need, size_t keep, cudaStr
   T* np = nullptr;
   cudaError_t rc = cudaMalloc(&np, (ncap + pad) * sizeof(T));
   if (rc != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc(%zu bytes): %s", (ncap + pad) * sizeof(T), cudaGetErrorString(rc));
+  if (ptr) CU(cudaStreamSynchronize(e->s_aux));  // CRC kernels may still read the old buffer
   if (ptr && keep) {
     CU(cudaStreamSynchronize(e->s_comp));
     CU(cudaMemcpyAsync(np, ptr, keep * sizeof(T), cudaMemcpyDeviceToDevice, s));
@@ -293,11 +295,12 @@ int inflate_new_blocks(ngsq_engine* e, uint32_t first_new, uint32_t n_new) {
       uint32_t* ns = nullptr;
       CU(cudaMalloc(&ns, cap * 4));
       CU(cudaMemsetAsync(ns, 0, cap * 4, e->s_comp));
-      if (e->d_status) { CU(cudaStreamSynchronize(e->s_comp)); cudaFree(e->d_status); }
+      if (e->d_status) { CU(cudaStreamSynchronize(e->s_comp)); CU(cudaStreamSynchronize(e->s_aux)); cudaFree(e->d_status); }
       e->d_status = ns;
     }
     if (cap > e->crcx_cap) {  // expected CRC32 per block (trailer values), checked right after each launch
       CU(cudaStreamSynchronize(e->s_comp));
+      CU(cudaStreamSynchronize(e->s_aux));
       if (e->d_crcx) cudaFree(e->d_crcx);
       e->d_crcx = nullptr;
       CU(cudaMalloc(&e->d_crcx, cap * 4));
@@ -314,7 +317,7 @@ int inflate_new_blocks(ngsq_engine* e, uint32_t first_new, uint32_t n_new) {
   CU(cudaMemcpyAsync(e->d_blocks + first_new, e->h_blocks.data() + first_new, n_new * sizeof(BlockDesc), cudaMemcpyHostToDevice, e->s_comp));
   if (e->n_launches >= ngsq_engine::kQueueSlots) return fail(e, NGSQ_E_ARG, "too many submits in one run (max %u)", ngsq_engine::kQueueSlots);
   ngsq_engine::InflateEvents ev{};
-  for (cudaEvent_t* x : {&ev.begin, &ev.decoded_from, &ev.decoded, &ev.end, &ev.crc_end}) CU(cudaEventCreate(x));
+  for (cudaEvent_t* x : {&ev.begin, &ev.decoded_from, &ev.decoded, &ev.end, &ev.crc_begin, &ev.crc_end}) CU(cudaEventCreate(x));
   CU(cudaEventRecord(ev.begin, e->s_comp));
   int rc;
   {
@@ -334,17 +337,20 @@ int inflate_new_blocks(ngsq_engine* e, uint32_t first_new, uint32_t n_new) {
   }
   if (rc) return rc;
   CU(cudaEventRecord(ev.end, e->s_comp));
-  // CRC32 of the new blocks against their trailers (what noodles-bgzf checks per block), launched
-  // per wave so that it overlaps the host-to-device copy of the next chunks
+  // CRC32 of the new blocks against their trailers (what noodles-bgzf checks per block), launched per
+  // wave on its own stream: it overlaps the host-to-device copy of the next chunks, the next wave and,
+  // for the last wave, the record scan and the facet kernel
+  CU(cudaStreamWaitEvent(e->s_aux, ev.end, 0));
+  CU(cudaEventRecord(ev.crc_begin, e->s_aux));
   if (e->cfg.flags & NGSQ_F_VERIFY_CRC) {
-    CU(cudaMemcpyAsync(e->d_crcx + first_new, e->h_crc.data() + first_new, (size_t)n_new * 4, cudaMemcpyHostToDevice, e->s_comp));
+    CU(cudaMemcpyAsync(e->d_crcx + first_new, e->h_crc.data() + first_new, (size_t)n_new * 4, cudaMemcpyHostToDevice, e->s_aux));
     const uint32_t grid = std::min<uint32_t>((n_new + kCrcThreads / 32 - 1) / (kCrcThreads / 32), (uint32_t)e->n_sm * 6);
-    crc32_kernel<<<grid, kCrcThreads, kCrcSmem, e->s_comp>>>(e->d_out, e->d_blocks + first_new, e->d_crcx + first_new, n_new, e->d_crc_tables,
-                                                               &e->d_flags->crc_bad);
+    crc32_kernel<<<grid, kCrcThreads, kCrcSmem, e->s_aux>>>(e->d_out, e->d_blocks + first_new, e->d_crcx + first_new, n_new, e->d_crc_tables,
+                                                            &e->d_flags->crc_bad);
     CU(cudaGetLastError());
     e->other_launches++;
   }
-  CU(cudaEventRecord(ev.crc_end, e->s_comp));
+  CU(cudaEventRecord(ev.crc_end, e->s_aux));
   e->inflate_events.push_back(ev);
   e->n_launches++;
   return NGSQ_OK;
@@ -360,6 +366,13 @@ int launch_pending(ngsq_engine* e, uint32_t upto) {
   int rc = inflate_new_blocks(e, e->launched, upto - e->launched);
   if (rc) return rc;
   e->launched = upto;
+  return NGSQ_OK;
+}
+
+// waits for the CRC kernels (own stream) and returns the number of blocks whose CRC32 did not match
+int crc_verdict(ngsq_engine* e, uint32_t* n_bad) {
+  CU(cudaStreamSynchronize(e->s_aux));
+  CU(cudaMemcpy(n_bad, &e->d_flags->crc_bad, 4, cudaMemcpyDeviceToHost));
   return NGSQ_OK;
 }
 
@@ -407,6 +420,7 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   e->n_sm = prop.multiProcessorCount;
   CUC(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
+  CUC(cudaStreamCreateWithFlags(&e->s_aux, cudaStreamNonBlocking));
   for (cudaEvent_t* ev : {&e->ev_start, &e->ev_a, &e->ev_b, &e->ev_c, &e->ev_d, &e->ev_e, &e->ev_f}) CUC(cudaEventCreate(ev));
   CUC(cudaMalloc(&e->d_queue, ngsq_engine::kQueueSlots * 4));
   CUC(cudaMalloc(&e->d_flags, sizeof(DevFlags)));
@@ -444,7 +458,7 @@ void ngsq_destroy(ngsq_engine* e) {
   cudaDeviceSynchronize();
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto ev : e->copy_events) cudaEventDestroy(ev);
-  for (auto& p : e->inflate_events) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.end, p.crc_end}) cudaEventDestroy(x);
+  for (auto& p : e->inflate_events) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
   for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_c, e->ev_d, e->ev_e, e->ev_f}) if (ev) cudaEventDestroy(ev);
   void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_res, e->d_out,
                   e->d_blocks, e->d_status, e->d_crcx, e->d_bitmap, e->d_queue, e->d_agree, e->d_out_off, e->d_coff, e->d_base, e->d_rec, e->d_first, e->d_landed,
@@ -453,6 +467,7 @@ void ngsq_destroy(ngsq_engine* e) {
   for (auto& sg : e->comp_segs) cudaFree(sg.ptr);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
+  if (e->s_aux) cudaStreamDestroy(e->s_aux);
   delete e;
 }
 
@@ -461,11 +476,12 @@ int ngsq_reset(ngsq_engine* e) {
   CU(cudaSetDevice(e->device));
   CU(cudaStreamSynchronize(e->s_copy));
   CU(cudaStreamSynchronize(e->s_comp));
+  CU(cudaStreamSynchronize(e->s_aux));
   for (auto ev : e->copy_events) cudaEventDestroy(ev);
   e->copy_events.clear();
   e->copy_upto.clear();
   e->launched = 0;
-  for (auto& p : e->inflate_events) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.end, p.crc_end}) cudaEventDestroy(x);
+  for (auto& p : e->inflate_events) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
   e->inflate_events.clear();
   e->h_blocks.clear(); e->h_coff.clear(); e->h_out_off.clear(); e->h_crc.clear();
   // keep the largest compressed segment, drop the rest
@@ -710,7 +726,11 @@ int ngsq_finish(ngsq_engine* e) {
       e->other_launches += 2;
       CU(cudaMemcpyAsync(&hf, e->d_flags, sizeof hf, cudaMemcpyDeviceToHost, s));
       CU(cudaStreamSynchronize(s));
-      if (hf.scan.chain) return fail(e, NGSQ_E_CHAIN, "record chain does not close on the shard's end offset");
+      if (hf.scan.chain) {
+        uint32_t nbad = 0;
+        if (hf.inflate_err == 0 && crc_verdict(e, &nbad) == NGSQ_OK && nbad) { e->finished = true; return fail(e, NGSQ_E_CRC, "%u BGZF block(s) failed the CRC32 check", nbad); }
+        return fail(e, NGSQ_E_CHAIN, "record chain does not close on the shard's end offset");
+      }
     }
   } else {
     CU(cudaEventRecord(e->ev_b, s));
@@ -728,7 +748,12 @@ int ngsq_finish(ngsq_engine* e) {
         return fail(e, NGSQ_E_BAD_BLOCK, "BGZF block at file offset %llu failed to inflate (%s)", (unsigned long long)e->h_coff[b],
                     st[b] == kBlkIsize ? "ISIZE mismatch" : st[b] == kBlkOverrun ? "output overrun / bad distance" : "invalid DEFLATE stream");
       }
-    if (hf.crc_bad) { e->finished = true; return fail(e, NGSQ_E_CRC, "%u BGZF block(s) failed the CRC32 check", hf.crc_bad); }
+    if (hf.scan.truncated || hf.scan.bad_record) {  // garbage bytes of a block that fails its CRC break the chain too: CRC first
+      uint32_t nbad = 0;
+      rc = crc_verdict(e, &nbad);
+      if (rc) return rc;
+      if (nbad) { e->finished = true; return fail(e, NGSQ_E_CRC, "%u BGZF block(s) failed the CRC32 check", nbad); }
+    }
     if (hf.scan.truncated) { e->finished = true; return fail(e, NGSQ_E_TRUNCATED, "record chain runs past the end of the submitted data"); }
     if (hf.scan.bad_record) { e->finished = true; return fail(e, NGSQ_E_BAD_RECORD, "malformed record length on the record chain"); }
     scan_counts_kernel<<<1, 1024, 0, s>>>(e->d_count, nb, e->d_base, &e->d_flags->n_records);
@@ -790,11 +815,16 @@ int ngsq_finish(ngsq_engine* e) {
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(e->ev_e, s));
+  // the step ends when the CRC stream is done too (its last event closes the device-timed region)
+  if (!e->inflate_events.empty()) CU(cudaStreamWaitEvent(s, e->inflate_events.back().crc_end, 0));
   e->h_res.resize(e->res_words);
   CU(cudaMemcpyAsync(e->h_res.data(), e->d_res, e->res_words * 8, cudaMemcpyDeviceToHost, s));
+  uint32_t crc_bad = 0;
+  CU(cudaMemcpyAsync(&crc_bad, &e->d_flags->crc_bad, 4, cudaMemcpyDeviceToHost, s));
   CU(cudaEventRecord(e->ev_f, s));
   CU(cudaStreamSynchronize(s));
   e->finished = true;
+  if (crc_bad) return fail(e, NGSQ_E_CRC, "%u BGZF block(s) failed the CRC32 check", crc_bad);
   e->h_qpos = (uint32_t)e->h_res[R_QUAL_POSITIONS];
   // stats
   ngsq_stats& st = e->stats;
@@ -808,7 +838,7 @@ int ngsq_finish(ngsq_engine* e) {
     cudaEventElapsedTime(&ms, p.begin, p.end); st.ms_inflate += ms;
     cudaEventElapsedTime(&ms, p.decoded_from, p.decoded); st.ms_inflate_decode += ms;
     cudaEventElapsedTime(&ms, p.decoded, p.end); st.ms_inflate_resolve += ms;
-    cudaEventElapsedTime(&ms, p.end, p.crc_end); crc_ms += ms;
+    cudaEventElapsedTime(&ms, p.crc_begin, p.crc_end); crc_ms += ms;
   }
   st.ms_crc = crc_ms;
   cudaEventElapsedTime(&st.ms_scan, e->ev_b, e->ev_c);

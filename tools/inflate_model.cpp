@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
   std::vector<uint32_t> bitmap(kBitmapWords);
   std::vector<uint8_t> out(65536 + 64), ref(65536);
   uint64_t hist_len[260] = {0}, n_blocks = 0, total_out = 0, total_in = 0, bad = 0, resolve_tokens = 0;
-  uint64_t dist_small = 0, dist_lt_len = 0, rounds_hist[34] = {0}, n_batches = 0, rounds_total = 0;
+  uint64_t dist_far = 0, dist_small = 0, dist_lt_len = 0, rounds_hist[34] = {0}, n_batches = 0, rounds_total = 0;
   size_t o = 0;
   while (o + 18 <= n && n_blocks < max_blocks) {
     const uint8_t* h = &buf[o];
@@ -167,7 +167,7 @@ int main(int argc, char** argv) {
             uint32_t p = w * 32 + bit;
             uint32_t tok = ob[p] | (ob[p + 1] << 8) | (ob[p + 2] << 16);
             uint32_t mlen = (tok & 255) + 3, dist = (tok >> 8) + 1;
-            if (mis == 0) { hist_len[mlen]++; resolve_tokens++; dist_small += dist < 4; dist_lt_len += dist < mlen; }
+            if (mis == 0) { hist_len[mlen]++; resolve_tokens++; dist_small += dist < 4; dist_lt_len += dist < mlen; dist_far += dist >= 1024 + 258; }
             for (uint32_t k = 0; k < mlen; ++k) ob[p + k] = ob[p + k - dist];
           }
         }
@@ -217,6 +217,7 @@ int main(int argc, char** argv) {
          (unsigned long long)ctr.stored, (unsigned long long)ctr.fixed, (double)ctr.symbols / ctr.headers);
   printf("stores: %llu chunk + %llu edge = %.3f per output byte\n", (unsigned long long)ctr.chunk_stores, (unsigned long long)ctr.edge_stores,
          (double)(ctr.chunk_stores + ctr.edge_stores) / total_out);
+  printf("dist >= 1282 (source before the resolve kernel's 1024-byte window): %.1f%% of matches\n", 100.0 * dist_far / (resolve_tokens ? resolve_tokens : 1));
   printf("dist<4: %.1f%% of matches, dist<len: %.1f%%\n", 100.0 * dist_small / (resolve_tokens ? resolve_tokens : 1), 100.0 * dist_lt_len / (resolve_tokens ? resolve_tokens : 1));
   printf("resolve batches %llu, mean dependency depth %.2f; depth histogram %%:", (unsigned long long)n_batches, (double)rounds_total / (n_batches ? n_batches : 1));
   for (int d = 1; d <= 33; ++d) if (rounds_hist[d]) printf(" %d:%.1f", d, 100.0 * rounds_hist[d] / n_batches);
