@@ -120,13 +120,13 @@ __device__ __forceinline__ void facet_prefetch(const uint8_t* sq, uint32_t ls, u
                                                uint32_t (&qb)[kQualPre], uint32_t (&gb)[3]) {
   // nothing here may consume a loaded value (no selects, no shifts): the loads must stay in flight
   // while the previous record is tallied
-  const uint8_t* ql = sq + (ls + 1) / 2;
+  const uint8_t* qlane = sq + (ls + 1) / 2 + lane;
   const uint32_t n_s = ls < qpos_smem ? ls : qpos_smem;
+  const uint32_t n_k = n_s > lane ? (n_s - lane + 31) >> 5 : 0;  // positions lane + 32k < n_s  <=>  k < n_k
 #pragma unroll
   for (uint32_t k = 0; k < kQualPre; ++k) {
-    const uint32_t i = lane + 32 * k;
     qb[k] = 0x100u;
-    if (i < n_s) qb[k] = __ldg(ql + i);
+    if (k < n_k) qb[k] = __ldg(qlane + 32 * k);
   }
   gb[0] = gb[1] = gb[2] = 0;
   if (gj != 0xFFFFFFFFu && lane < 25) {
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
   const uint32_t n_sm = qtab_words * warps_in_cta + kTlenPad + kGcPad + kCigWords;
   uint32_t* my_qwords = sm + qtab_words * (threadIdx.x >> 5);          // this warp's private table
   uint8_t* my_qtab = reinterpret_cast<uint8_t*>(my_qwords);
+  uint8_t* my_qrow = my_qtab + (threadIdx.x & 31) * kQualRowBytes;  // row of position `lane`; position lane + 32k is 32k rows further
   uint32_t steps_since_flush = 0;
   for (uint32_t i = threadIdx.x; i < n_sm; i += blockDim.x) sm[i] = 0;
   __syncthreads();
@@ -329,12 +330,11 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
           const uint32_t k0 = gj + 4 * lane;
           const uint32_t v = (gb[0] << 16) | (gb[1] << 8) | gb[2];
           const uint32_t u = (v >> ((k0 & 1) ? 4 : 8)) & 0xFFFFu;  // first base in the top nibble
-#pragma unroll
-          for (int jb = 0; jb < 4; ++jb) {
-            const uint32_t code = (u >> (12 - 4 * jb)) & 15u;
-            gc += (0x0014u >> code) & 1u;  // C = 2, G = 4
-            at += (0x0102u >> code) & 1u;  // A = 1, T = 8
-          }
+          // A, C, G, T are the one-hot codes 1, 2, 4, 8: per nibble, C|G <=> exactly one of bits 1, 2 and
+          // neither of bits 0, 3; A|T <=> exactly one of bits 0, 3 and neither of bits 1, 2 (all four nibbles at once)
+          const uint32_t b1 = u >> 1, b2 = u >> 2, b3 = u >> 3;
+          gc = __popc((b1 ^ b2) & ~(u | b3) & 0x1111u);
+          at = __popc((u ^ b3) & ~(b1 | b2) & 0x1111u);
         }
         gc = __reduce_add_sync(0xFFFFFFFFu, gc);
         at = __reduce_add_sync(0xFFFFFFFFu, at);
@@ -344,19 +344,20 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
       // ---- Quality scores (quality_scores.rs:37-49; presence rule SURVEY App. D.5): one pass.
       // Qualities are present unless every byte is 0xFF; a present string must be <= 93 throughout,
       // so increments for bytes <= 93 are exact whenever the run does not fail.
-      bool any_real = false, any_big = false;
+      // per lane: smallest byte seen (0x100 = none) and largest real byte; "present" <=> some byte != 0xFF,
+      // "too big" <=> some byte in 94..255 — two min/max per position instead of compares and branches
+      uint32_t q_min = 0x100u, q_max = 0;
 #pragma unroll
       for (uint32_t k = 0; k < kQualPre; ++k) {
         const uint32_t q = qb[k];
-        if (q <= 0xFF) {
-          any_real |= q != 0xFF;
-          if (q > 93) any_big = true;
-          else {
-            uint8_t* c = my_qtab + (lane + 32 * k) * kQualRowBytes + q;  // private to this warp; lanes hold distinct positions
-            *c = (uint8_t)(*c + 1);
-          }
+        q_min = min(q_min, q);
+        q_max = max(q_max, q & 0xFFu);  // the "beyond the string" marker 0x100 counts as 0 here
+        if (q <= 93) {
+          uint8_t* c = my_qrow + k * (32 * kQualRowBytes) + q;  // private to this warp; lanes hold distinct positions
+          *c = (uint8_t)(*c + 1);
         }
       }
+      bool any_real = q_min < 0xFFu, any_big = q_max > 93;
       const uint32_t n_s = ls < P.qpos_smem ? ls : P.qpos_smem;
       for (uint32_t i = 32 * kQualPre + lane; i < n_s; i += 32) {  // shared-memory positions beyond the prefetched ones
         const uint32_t q = __ldg(ql + i);
