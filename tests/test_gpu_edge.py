@@ -138,6 +138,25 @@ def test_crc_mismatch_is_reported():
     engine_ints(as_u8(bytes(b)), crc=False)
 
 
+def test_corrupt_payload_with_valid_deflate_is_a_crc_error_in_every_launch_shape():
+    """Bytes changed inside a stored DEFLATE block still inflate, so only the CRC32 check (own stream, one
+    launch per wave) can reject them, and it must win over the record-chain errors the garbage causes —
+    with one inflate launch and with many (chunked submits, 64-block launches)."""
+    payload = 4096
+    bam, bai = write_bam(REFS, _records(seed=11), block_payload=payload, level=0)
+    b = bytearray(bam)
+    first = len(bgzf_block(header_bytes(REFS), 0))
+    # third record block: skip 18 bytes of gzip header + 5 of the stored-block header, flip payload bytes
+    off = first
+    for _ in range(2):
+        off += struct.unpack_from("<H", b, off + 16)[0] + 1
+    for k in range(off + 18 + 5 + 40, off + 18 + 5 + 48):
+        b[k] ^= 0x5A
+    assert _engine_error(bytes(b)).code == -5
+    assert _engine_error(bytes(b), chunk_bytes=20000, launch_blocks=64).code == -5
+    assert _engine_error(bytes(b), chunk_bytes=9000, launch_blocks=2).code == -5
+
+
 def test_isize_mismatch_is_bad_block():
     bam, bai = write_bam(REFS, _records(seed=9), block_payload=5000)
     b = bytearray(bam)
