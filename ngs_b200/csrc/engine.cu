@@ -191,11 +191,6 @@ int grow(ngsq_engine* e, T*& ptr, size_t& cap, size_t need, size_t keep, cudaStr
 int launch_inflate(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_t* out, uint32_t* queue, uint32_t* status,
                    uint32_t* bitmap, cudaStream_t s, cudaEvent_t ev_decode_from = nullptr, cudaEvent_t ev_decoded = nullptr) {
   if (!n) return NGSQ_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU(cudaFuncSetAttribute(inflate_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem));
-    attr_set = true;
-  }
   CU(cudaMemsetAsync(bitmap, 0, (size_t)n * kBitmapWords * 4, s));
   const uint32_t per_cta = kDecThreads;
   uint32_t grid = std::min<uint32_t>((n + per_cta - 1) / per_cta, (uint32_t)e->n_sm);
@@ -427,7 +422,10 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   CUC(cudaMalloc(&e->d_queue, ngsq_engine::kQueueSlots * 4));
   CUC(cudaMalloc(&e->d_flags, sizeof(DevFlags)));
   CUC(cudaMalloc(&e->d_crc_tables, sizeof(CrcTables)));
+  // opt-in shared memory sizes are per device: set them for this engine's device (several engines of
+  // one process may sit on different GPUs)
   CUC(cudaFuncSetAttribute(crc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCrcSmem));
+  CUC(cudaFuncSetAttribute(inflate_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem));
   {
     CrcTables t;
     crc_make_tables(t);
