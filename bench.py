@@ -130,12 +130,14 @@ def cpu_sample(args, total_records, level):
     for c in order:
         if per_contig[c] == 0:
             continue
-        if n and n + per_contig[c] > args.cpu_sample * 1.25:
+        if n >= args.cpu_sample:
+            break
+        # once past half the target, do not overshoot it by more than half (the first real contig is always taken:
+        # at 600 M records the smallest chromosome alone holds 9 M)
+        if n > args.cpu_sample * 0.5 and n + per_contig[c] > args.cpu_sample * 1.5:
             break
         mask |= 1 << c
         n += per_contig[c]
-        if n >= args.cpu_sample:
-            break
     bam, bai, info = ffi.synth_bam(1, total_records, level=level, contig_mask=mask, with_tail=False)
     contigs = [c for c in range(len(per_contig)) if mask >> c & 1]
     desc = (f"{info['n_records']} records = contigs {contigs} of the {total_records}-record WGS-shaped BAM at full depth "
