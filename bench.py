@@ -151,7 +151,7 @@ def run_reference(args, rank, emit):
         return
     from helpers import oracle_ints
     from ngs_b200 import ffi
-    total = args.records or (100_000_000 if args.gpus == 1 else 75_000_000 * args.gpus)
+    total = (args.records or (100_000_000 if args.gpus == 1 else 75_000_000)) * args.gpus  # the logical BAM of the GPU arm
     level = args.level if args.level >= 0 else (1 if total >= 20_000_000 else 6)
     bam, bai, info, desc = cpu_sample(args, total, level)
     n = info["n_records"]
