@@ -1,7 +1,8 @@
 """CPU check of the inflate kernel's decoder logic: ngs_b200/csrc/inflate_lane.cuh (the per-lane
 canonical Huffman decoder the CUDA decode kernel runs, compiled for the host by
-tools/inflate_model.cpp) plus a scalar restatement of the resolve pass must reproduce zlib's bytes on
-stored / fixed / dynamic / multi-block DEFLATE streams at two output alignments.  Test tooling only:
+tools/inflate_model.cpp) plus the resolve pass — a scalar one at the first output alignment, a lane-by-lane
+restatement of the resolve kernel's warp algorithm (32-token batches, dependency masks, rounds, 8-byte copy
+steps) at the second — must reproduce zlib's bytes on stored / fixed / dynamic / multi-block DEFLATE streams.  Test tooling only:
 nothing under ngs_b200/ links or calls this."""
 import os
 import struct

@@ -18,6 +18,75 @@
 
 using namespace ngsq;
 
+// Lane-by-lane restatement of inflate_resolve_kernel (inflate2.cuh): 1024-byte super-windows, 32-token
+// batches, dependency masks from two binary searches over the sorted destination ranges, rounds, and the
+// 8-byte copy steps with distance doubling.  Reads of a round see memory as it was when the round
+// started only where the kernel guarantees it (ready lanes never read what another ready lane writes).
+static void resolve_copy_model(uint8_t* dst, uint32_t mlen, uint32_t dist) {
+  uint32_t D = dist;
+  for (uint32_t done = 0; done < mlen;) {
+    const uint32_t n = std::min(std::min(8u, D), mlen - done);
+    uint8_t tmp[8];
+    memcpy(tmp, dst + done - D, n);  // the kernel loads the 8 bytes first, then stores n of them
+    memcpy(dst + done, tmp, n);
+    done += n;
+    if (D < 8) D <<= 1;
+  }
+}
+
+static uint64_t g_rounds = 0, g_batches = 0;
+
+static void resolve_block_model(uint8_t* ob, uint32_t isize, const uint32_t* bitmap) {
+  const uint32_t n_sw = (isize + 1023) >> 10;
+  std::vector<uint32_t> list;
+  for (uint32_t sw = 0; sw < n_sw; ++sw) {
+    list.clear();
+    for (uint32_t lane = 0; lane < 32; ++lane)
+      for (uint32_t m = bitmap[sw * 32 + lane]; m; m &= m - 1) list.push_back((sw << 10) + (lane << 5) + __builtin_ctz(m));
+    const uint32_t total = (uint32_t)list.size();
+    for (uint32_t base = 0; base < total; base += 32) {
+      uint32_t pos[32], mlen[32], dist[32], dpos[32], dend[32], s_lo[32], s_hi[32], dep[32];
+      bool active[32];
+      for (uint32_t l = 0; l < 32; ++l) {
+        active[l] = base + l < total;
+        pos[l] = active[l] ? list[base + l] : 0xFFFFu;
+        uint32_t tok = 0;
+        if (active[l]) tok = ob[pos[l]] | (ob[pos[l] + 1] << 8) | (ob[pos[l] + 2] << 16);  // tokens are read before any copy of the batch
+        mlen[l] = (tok & 255u) + 3u;
+        dist[l] = (tok >> 8) + 1u;
+        dpos[l] = active[l] ? pos[l] : 0x20000u;
+        dend[l] = active[l] ? pos[l] + mlen[l] : 0x20000u;
+        s_lo[l] = pos[l] - dist[l];
+        s_hi[l] = s_lo[l] + std::min(mlen[l], dist[l]);
+      }
+      for (uint32_t l = 0; l < 32; ++l) {
+        uint32_t lo = 0, hi = 0;
+        for (int step = 32; step; step >>= 1) {
+          const uint32_t il = lo + step - 1, ih = hi + step - 1;
+          const uint32_t e = dend[il & 31], p2 = dpos[ih & 31];
+          if (il < 32 && e <= s_lo[l]) lo += step;
+          if (ih < 32 && p2 < s_hi[l]) hi += step;
+        }
+        dep[l] = 0;
+        if (active[l] && hi > lo) dep[l] = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u) & ((1u << l) - 1u);
+      }
+      uint32_t done = 0;
+      for (uint32_t l = 0; l < 32; ++l) if (!active[l]) done |= 1u << l;
+      g_batches++;
+      while (done != 0xFFFFFFFFu) {
+        uint32_t ready = 0;
+        for (uint32_t l = 0; l < 32; ++l) if (!((done >> l) & 1u) && (dep[l] & ~done) == 0) ready |= 1u << l;
+        if (!ready) { fprintf(stderr, "resolve model: no lane ready\n"); exit(1); }
+        // all ready lanes copy "at once": run them in reverse lane order to expose a lane that wrongly
+        // depends on a lower ready lane's output
+        for (int l = 31; l >= 0; --l) if ((ready >> l) & 1u) resolve_copy_model(ob + pos[l], mlen[l], dist[l]);
+        done |= ready;
+        g_rounds++;
+      }
+    }
+  }
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { fprintf(stderr, "usage: %s file.bam [max_blocks]\n", argv[0]); return 2; }
   FILE* f = fopen(argv[1], "rb");
@@ -158,8 +227,9 @@ int main(int argc, char** argv) {
             }
           }
         }
-        // resolve pass (scalar, stream order)
-        for (uint32_t w = 0; w < kBitmapWords; ++w) {
+        // resolve pass: scalar in stream order for the first alignment, the warp algorithm of the kernel for the second
+        if (mis != 0) resolve_block_model(ob, isize, bitmap.data());
+        for (uint32_t w = 0; w < kBitmapWords && mis == 0; ++w) {
           uint32_t m = bitmap[w];
           while (m) {
             uint32_t bit = __builtin_ctz(m);
@@ -222,6 +292,8 @@ int main(int argc, char** argv) {
   printf("resolve batches %llu, mean dependency depth %.2f; depth histogram %%:", (unsigned long long)n_batches, (double)rounds_total / (n_batches ? n_batches : 1));
   for (int d = 1; d <= 33; ++d) if (rounds_hist[d]) printf(" %d:%.1f", d, 100.0 * rounds_hist[d] / n_batches);
   printf("\n");
+  printf("warp-algorithm resolve (second alignment): %llu batches, %.2f rounds per batch\n", (unsigned long long)g_batches,
+         (double)g_rounds / (g_batches ? g_batches : 1));
   printf("match length histogram (cumulative %%):");
   uint64_t cum = 0;
   for (int l = 3; l <= 258; ++l) {

@@ -17,4 +17,8 @@ s = sum(tot.values())
 ie = hdr.index("Instructions Executed")
 print("instructions", sum(int(r[ie] or 0) for r in body), "samples", s)
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
-    if v: print(f"{k[6:]:24s} {100*v/s:6.2f}%")
+    if v:
+        try:
+            print(f"{k[6:]:24s} {100*v/s:6.2f}%")
+        except BrokenPipeError:
+            break
