@@ -619,6 +619,165 @@ int64_t oracle_inflate_all(const uint8_t* bgzf, size_t n, uint8_t* out, size_t c
   return rc < 0 ? -1 : (int64_t)w;
 }
 
+/* ------------------------------------------------------------ Edits
+ * Oracle FIRST for the next row of the scope table: no device path consumes this yet.
+ * Restates src/utils/cigar.rs:6-23 (which ops consume what), src/utils/alignment.rs:13-126
+ * (flatten + ReferenceRecordStepThrough::stepthrough / edits) and the Edits facet
+ * src/qc/sequence_based/edits.rs:170-344 (supports every sequence name; setup loads the contig from
+ * the FASTA; process; teardown = VAF histogram in f32; aggregate = the two means).
+ * Pinned by the reference's own tests src/utils/alignment.rs:134-202 (tests/test_oracle_edits.py). */
+static int edits_consumes_reference(uint32_t k) { return k == 0 || k == 2 || k == 3 || k == 7 || k == 8; } /* M D N = X */
+static int edits_consumes_sequence(uint32_t k) { return k == 0 || k == 1 || k == 4 || k == 7 || k == 8; }  /* M I S = X */
+
+/* Bases are compared as noodles `Base` values: one code per letter of "=ACMGRSVTWYHKDBN" (the BAM
+ * 4-bit codes).  reference/record: arrays of those codes.  cigar: BAM ops (len << 4 | kind).
+ * on_match(ctx, reference_ptr, is_edit) is called for every M position (edits.rs:274-292).
+ * Returns 0, or: 1 "...consume a reference base, but no such base was found", 2 "...consume a record
+ * base, but no such base was found", 3 "reference sequence was not fully consumed", 4 "record sequence
+ * was not fully consumed" (alignment.rs:60-106), 6 invalid CIGAR op. */
+typedef void (*edits_cb)(void* ctx, uint64_t reference_ptr, int is_edit);
+static int edits_stepthrough(const uint8_t* reference, uint64_t n_reference, const uint8_t* record, uint64_t n_record,
+                             const uint32_t* cigar, uint64_t n_ops, uint64_t* edits, edits_cb on_match, void* ctx) {
+  uint64_t record_ptr = 0, reference_ptr = 0, e = 0;
+  for (uint64_t o = 0; o < n_ops; ++o) {
+    uint32_t op; memcpy(&op, (const uint8_t*)cigar + 4 * o, 4);
+    uint32_t kind = op & 15, len = op >> 4;
+    if (kind > 8) return 6;
+    for (uint32_t t = 0; t < len; ++t) { /* the flattened CIGAR, one kind per step (alignment.rs:13-25,53) */
+      int cr = edits_consumes_reference(kind), cs = edits_consumes_sequence(kind);
+      int rb = -1, qb = -1; /* None */
+      if (cr) { if (reference_ptr >= n_reference) return 1; rb = reference[reference_ptr]; }
+      if (cs) { if (record_ptr >= n_record) return 2; qb = record[record_ptr]; }
+      if (kind == 0) { /* Kind::Match only: "=" and "X" are not counted (edits.rs:274) */
+        int is_edit = rb != qb;
+        e += is_edit;
+        if (on_match) on_match(ctx, reference_ptr, is_edit);
+      }
+      if (cr) reference_ptr++;
+      if (cs) record_ptr++;
+    }
+  }
+  if (reference_ptr != n_reference) return 3;
+  if (record_ptr != n_record) return 4;
+  *edits = e;
+  return 0;
+}
+int oracle_stepthrough_edits(const uint8_t* reference, uint64_t n_reference, const uint8_t* record, uint64_t n_record,
+                             const uint32_t* cigar, uint64_t n_ops, uint64_t* edits) {
+  return edits_stepthrough(reference, n_reference, record, n_record, cigar, n_ops, edits, NULL, NULL);
+}
+
+/* noodles Base::try_from(char): the sixteen upper-case letters of the BAM code table, anything else
+ * (lower case included) is an error and aborts the run (edits.rs:259-265).  Returns the 4-bit code or -1. */
+static int edits_base_code(uint8_t ch) {
+  static const char tab[] = "=ACMGRSVTWYHKDBN";
+  for (int i = 0; i < 16; ++i) if ((uint8_t)tab[i] == ch) return i;
+  return -1;
+}
+
+typedef struct {
+  hist_t read_one, read_two, vaf;      /* Histogram::default() = 0..=512 (histogram.rs:472-481), VAF 0..=100 */
+  double mean_read_one, mean_read_two; /* aggregate (edits.rs:336-344) */
+  uint64_t records;                    /* records that reached the step-through */
+} edits_t;
+typedef struct { uint64_t* refs; uint64_t* alts; uint64_t start; } edits_pos_ctx;
+static void edits_on_match(void* c, uint64_t reference_ptr, int is_edit) {
+  edits_pos_ctx* x = c;
+  uint64_t p = x->start + reference_ptr; /* 1-based reference position (edits.rs:276-278) */
+  if (is_edit) x->alts[p]++; else x->refs[p]++;
+}
+
+/* fasta: text of a FASTA file whose record names (first word after '>') are looked up per contig. */
+static int edits_find_contig(const char* fasta, size_t n, const char* name, uint8_t** codes, uint64_t* len) {
+  size_t i = 0, ln = strlen(name);
+  while (i < n) {
+    if (fasta[i] != '>') { while (i < n && fasta[i] != '\n') ++i; ++i; continue; }
+    size_t b = i + 1, e = b;
+    while (e < n && fasta[e] != '\n' && fasta[e] != ' ' && fasta[e] != '\t') ++e;
+    size_t eol = e; while (eol < n && fasta[eol] != '\n') ++eol;
+    int hit = (e - b == ln) && !memcmp(fasta + b, name, ln);
+    i = eol + 1;
+    size_t s = i;
+    while (i < n && fasta[i] != '>') { while (i < n && fasta[i] != '\n') ++i; ++i; }
+    if (!hit) continue;
+    uint8_t* out = malloc(i - s + 1); uint64_t k = 0;
+    for (size_t q = s; q < i && q < n; ++q) {
+      uint8_t ch = (uint8_t)fasta[q];
+      if (ch == '\n' || ch == '\r') continue;
+      out[k++] = ch; /* kept as characters: conversion to Base happens per record slice (edits.rs:259-265) */
+    }
+    *codes = out; *len = k;
+    return 0;
+  }
+  return -1;
+}
+
+void* oracle_edits_run(const uint8_t* bam, size_t bam_len, const uint8_t* bai, size_t bai_len, const char* fasta, size_t fasta_len) {
+  g_err[0] = 0;
+  edits_t* E = calloc(1, sizeof *E);
+  hist_init(&E->read_one, 512); hist_init(&E->read_two, 512); hist_init(&E->vaf, 100);
+  bgzf_t* rd = malloc(sizeof *rd); recbuf_t rb = {malloc(1 << 16), 1 << 16}; rec_t rec;
+  ref_t* refs; uint32_t n_ref;
+  bgzf_open(rd, bam, bam_len);
+  if (read_header(rd, &refs, &n_ref)) return NULL;
+  bai_t B; if (!bai || bai_parse(bai, bai_len, &B)) { if (!g_err[0]) snprintf(g_err, sizeof g_err, "missing BAM index"); return NULL; }
+  for (uint32_t c = 0; c < n_ref; ++c) { /* pass 2 driver, command.rs:356-397; supports_sequence_name is always true (edits.rs:178-180) */
+    uint64_t L = refs[c].len;
+    uint8_t* seq; uint64_t seq_len;
+    if (edits_find_contig(fasta, fasta_len, refs[c].name, &seq, &seq_len)) { snprintf(g_err, sizeof g_err, "sequence %s not found in reference FASTA.", refs[c].name); return NULL; }
+    uint64_t* refs_pp = calloc(L + 1, 8); uint64_t* alts_pp = calloc(L + 1, 8); /* zero_based_with_capacity(seq_length) */
+    chunk_t* ch; size_t nch = bai_query(&B, c, 0, (int64_t)L, &ch);
+    for (size_t k = 0; k < nch; ++k) {
+      int src = bgzf_seek(rd, ch[k].beg); if (src < 0) return NULL; if (src == 0) break;
+      while (bgzf_tell(rd) < ch[k].end) {
+        int rc = read_record(rd, &rb, &rec, n_ref); if (rc < 0) return NULL; if (rc == 0) break;
+        if (rec.ref_id != (int32_t)c || rec.pos < 0) continue;
+        uint64_t start = (uint64_t)rec.pos + 1, end = start + rec.span - 1;
+        if (end == 0) continue;
+        if (!(start <= L && end >= 1)) continue;
+        if (rec.flag & (0x4 | 0x400)) continue; /* unmapped or duplicate (edits.rs:227-229) */
+        /* reference slice start .. start + span, 1-based, end exclusive (edits.rs:241-243,259-262): out of the
+         * FASTA sequence -> the reference unwraps a None and panics */
+        if (start - 1 + rec.span > seq_len) { snprintf(g_err, sizeof g_err, "record reaches past the end of the reference sequence"); return NULL; }
+        uint8_t* rcodes = malloc(rec.span + 1);
+        for (uint32_t t = 0; t < rec.span; ++t) {
+          int code = edits_base_code(seq[start - 1 + t]);
+          if (code < 0) { snprintf(g_err, sizeof g_err, "invalid base in the reference sequence"); return NULL; }
+          rcodes[t] = (uint8_t)code;
+        }
+        uint8_t* qcodes = malloc(rec.l_seq + 1);
+        for (uint32_t t = 0; t < rec.l_seq; ++t) qcodes[t] = (t & 1) ? (rec.seq[t >> 1] & 15) : (rec.seq[t >> 1] >> 4);
+        edits_pos_ctx ctx = {refs_pp, alts_pp, start};
+        uint64_t edits = 0;
+        int st = edits_stepthrough(rcodes, rec.span, qcodes, rec.l_seq, rec.cigar, rec.n_cigar, &edits, edits_on_match, &ctx);
+        free(rcodes); free(qcodes);
+        if (st) { snprintf(g_err, sizeof g_err, "step-through failed (%d)", st); return NULL; }
+        /* increment(edits).unwrap(): more than 512 edits panics the reference (edits.rs:296-300) */
+        if (hist_inc_by((rec.flag & 0x40) ? &E->read_one : &E->read_two, edits, 1)) { snprintf(g_err, sizeof g_err, "more than 512 edits in one read"); return NULL; }
+        E->records++;
+      }
+    }
+    free(ch);
+    for (uint64_t i = 0; i <= L; ++i) { /* teardown, edits.rs:318-334 */
+      uint64_t r = refs_pp[i], a = alts_pp[i], t = r + a;
+      if (!t) continue;
+      float vaf = (float)a / (float)t;
+      if (hist_inc_by(&E->vaf, (uint64_t)(vaf * 100.0f), 1)) return NULL;
+    }
+    free(refs_pp); free(alts_pp); free(seq);
+  }
+  E->mean_read_one = hist_mean(&E->read_one);
+  E->mean_read_two = hist_mean(&E->read_two);
+  free(rd); free(rb.buf);
+  return E;
+}
+void oracle_edits_get(void* p, uint64_t read_one[513], uint64_t read_two[513], uint64_t vaf[101], double means[2], uint64_t* records) {
+  edits_t* E = p;
+  memcpy(read_one, E->read_one.v, 513 * 8); memcpy(read_two, E->read_two.v, 513 * 8); memcpy(vaf, E->vaf.v, 101 * 8);
+  means[0] = E->mean_read_one; means[1] = E->mean_read_two; *records = E->records;
+}
+
+
 #ifdef ORACLE_MAIN
 static uint8_t* slurp(const char* path, size_t* n) {
   FILE* f = fopen(path, "rb"); if (!f) return NULL;
