@@ -125,7 +125,7 @@ struct ngsq_engine {
   uint32_t* d_status = nullptr;
   uint32_t* d_crcx = nullptr;    // expected CRC32 of every block
   size_t crcx_cap = 0;
-  uint32_t* d_bitmap = nullptr;  // v2 inflate: one bit per inflated byte, kBitmapWords per block
+  uint32_t* d_bitmap = nullptr;  // inflate: one bit per inflated byte ("a match starts here"), kBitmapWords per block
   size_t bitmap_cap = 0;         // blocks
   uint32_t* d_queue = nullptr;
   uint64_t* d_agree = nullptr;  // 3 words exchanged before the reduce

@@ -6,10 +6,11 @@
 //
 // Two phases per 32 records (see facets_kernel): header-derived facets with one record per lane,
 // per-base facets with one record per warp step.  Flag-derived counters: lane k owns counter k
-// and adds the popcount of a ballot of bit k: no atomics for General / record tallies.  Histograms (tlen, gc, per-position quality,
-// CIGAR kinds) are privatised in shared memory per CTA and flushed once with 64-bit global
-// reductions.  Quality positions beyond the shared-memory table (long reads) go straight to
-// the L2-resident global table.  Coverage is two signed global reductions per record into the
+// and adds the popcount of a ballot of bit k: no atomics for General / record tallies.  The tlen, gc
+// and CIGAR-kind histograms are privatised in shared memory per CTA and flushed once with 64-bit
+// global reductions; quality-by-position lives in one private table of 8-bit counters per WARP
+// (plain load/add/store, flushed every 224 records).  Quality positions beyond the shared-memory
+// table (long reads) go straight to the L2-resident global table.  Coverage is two signed global reductions per record into the
 // contig's int32 difference array (coverage is span-based: SURVEY F6).
 #pragma once
 #include <cstdint>

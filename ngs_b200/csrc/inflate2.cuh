@@ -1,4 +1,4 @@
-// K2 (v2) — BGZF inflate as two kernels (reference: the inflate noodles-bgzf/miniz_oxide perform
+// K2 — BGZF inflate as two kernels (reference: the inflate noodles-bgzf/miniz_oxide perform
 // under bam::Reader, src/utils/formats/bam.rs:41-44, src/qc/command.rs:305 and :350).
 //
 //   inflate_decode_kernel   one BGZF block per LANE: 32 independent Huffman decoders per warp
