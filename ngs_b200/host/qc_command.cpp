@@ -116,9 +116,11 @@ int app(const QcArgs& args, const ReferenceGenome& genome, const std::string& ou
   std::vector<uint32_t> ref_len;
   for (auto& rs : header.reference_sequences) ref_len.push_back(rs.length);
   for (uint32_t i = 0; i < n_dev; ++i) {
+    // the same mask on every engine: the packed result buffer (the NCCL payload) is laid out from it, and a
+    // contig outside an engine's shard simply stays untouched there (ngsq_reduce rejects differing layouts)
     std::vector<uint8_t> enabled(ref_len.size(), 0);
     for (auto& f : facets.sequence_based)
-      for (uint32_t c : shards[i].contigs)
+      for (uint32_t c = 0; c < ref_len.size(); ++c)
         if (f->supports_sequence_name(header.reference_sequences[c].name)) enabled[c] = 1;
     check(engines[i], ngsq_set_references(engines[i], (uint32_t)ref_len.size(), ref_len.data(), enabled.data()));
   }
