@@ -778,6 +778,122 @@ void oracle_edits_get(void* p, uint64_t read_one[513], uint64_t read_two[513], u
 }
 
 
+/* ------------------------------------------------------------ Genomic Features facet
+ * Oracle first, like Edits: no device path consumes this yet.  Restates
+ *   src/qc/record_based/features.rs:115-242 (process), 244-262 (summarize), 270-355 (try_from),
+ *   src/qc/record_based/features/utils.rs:33-43 (strand parse), src/utils/formats/gff.rs (plain-text GFF only here).
+ * Third-party behaviour restated from the published crates (absent from /root/reference, Cargo.lock pins):
+ *   rust-lapper 1.1.0: Lapper::new sorts intervals by (start, stop); find(start, stop) yields, in that order, every
+ *     interval with iv.start < stop && iv.stop > start (half-open);
+ *   noodles-gff (noodles 0.34.0): records() skips comments and directives, ends at ##FASTA, and the facet unwraps every
+ *     record, so a malformed line aborts; Display of a strand is "+", "-", "." or "?".
+ * Reference quirks kept: a feature's GFF end (inclusive) is used as an exclusive stop, so its last base does not count;
+ * the query is [start, start + span + 1) with the 1-based start, two bases past the last aligned base. */
+typedef struct { uint64_t start, stop; uint8_t is5, is3, iscds, isgene, isexon; } feat_iv;
+typedef struct { feat_iv* v; size_t n, cap; } feat_list;
+typedef struct {
+  uint64_t utr5, utr3, cds, intergenic, exonic, intronic, processed, ignored_flags, ignored_nonprimary;
+  double ignored_flags_pct, ignored_nonprimary_pct;
+} features_t;
+static void feat_push(feat_list* l, feat_iv iv) { if (l->n == l->cap) { l->cap = l->cap ? l->cap * 2 : 64; l->v = realloc(l->v, l->cap * sizeof *l->v); } l->v[l->n++] = iv; }
+static int feat_cmp(const void* a, const void* b) {
+  const feat_iv *x = a, *y = b;
+  if (x->start != y->start) return x->start < y->start ? -1 : 1;
+  if (x->stop != y->stop) return x->stop < y->stop ? -1 : 1;
+  return 0;
+}
+static int feat_parse_pos(const char* s, size_t n, uint64_t* out) { /* noodles Position: decimal, >= 1 */
+  if (!n || n > 18) return -1;
+  uint64_t v = 0;
+  for (size_t i = 0; i < n; ++i) { if (s[i] < '0' || s[i] > '9') return -1; v = v * 10 + (uint64_t)(s[i] - '0'); }
+  if (!v) return -1;
+  *out = v; return 0;
+}
+static int feat_eq(const char* s, size_t n, const char* name) { return strlen(name) == n && !memcmp(s, name, n); }
+
+/* names: five_prime_utr, three_prime_utr, coding_sequence, exon, gene (command.rs:78-101 defaults
+ * "five_prime_UTR", "three_prime_UTR", "CDS", "exon", "gene") */
+void* oracle_features_run(const uint8_t* bam, size_t bam_len, const char* gff, size_t gff_len, const char* const names[5], uint64_t n_records) {
+  g_err[0] = 0;
+  features_t* F = calloc(1, sizeof *F);
+  bgzf_t* rd = malloc(sizeof *rd); recbuf_t rb = {malloc(1 << 16), 1 << 16}; rec_t rec;
+  ref_t* refs; uint32_t n_ref;
+  bgzf_open(rd, bam, bam_len);
+  if (read_header(rd, &refs, &n_ref)) return NULL;
+  /* try_from: one (exonic translation, gene region) pair of lists per primary contig of the header */
+  feat_list* utr = calloc(n_ref ? n_ref : 1, sizeof *utr); feat_list* gene = calloc(n_ref ? n_ref : 1, sizeof *gene);
+  size_t o = 0;
+  while (o < gff_len) {
+    size_t e = o; while (e < gff_len && gff[e] != '\n') ++e;
+    size_t n = e - o; const char* ln = gff + o; o = e + 1;
+    if (n && ln[n - 1] == '\r') --n;
+    if (n >= 7 && !memcmp(ln, "##FASTA", 7)) break;
+    if (n && ln[0] == '#') continue;
+    const char* f[9]; size_t fl[9]; int nf = 0; size_t b = 0;
+    for (size_t i = 0; i <= n && nf < 9; ++i) if (i == n || ln[i] == '\t') { f[nf] = ln + b; fl[nf] = i - b; ++nf; b = i + 1; }
+    uint64_t start, stop;
+    if (nf < 9 || b <= n || feat_parse_pos(f[3], fl[3], &start) || feat_parse_pos(f[4], fl[4], &stop)) { snprintf(g_err, sizeof g_err, "invalid GFF record"); return NULL; }
+    uint32_t c = n_ref;
+    for (uint32_t i = 0; i < n_ref; ++i) if (refs[i].primary && feat_eq(f[0], fl[0], refs[i].name)) { c = i; break; }
+    if (c == n_ref) continue; /* only primary-assembly sequence names are tabulated (features.rs:297-301) */
+    if (!(fl[6] == 1 && (f[6][0] == '+' || f[6][0] == '-'))) { /* utils.rs:36-42, parsed before the type is looked at */
+      snprintf(g_err, sizeof g_err, "attempted to parse strand from value: %.*s", (int)fl[6], f[6]); return NULL; }
+    feat_iv iv = {start, stop, (uint8_t)feat_eq(f[2], fl[2], names[0]), (uint8_t)feat_eq(f[2], fl[2], names[1]), (uint8_t)feat_eq(f[2], fl[2], names[2]),
+                  (uint8_t)feat_eq(f[2], fl[2], names[4]), (uint8_t)feat_eq(f[2], fl[2], names[3])};
+    if (iv.is5 || iv.is3 || iv.iscds) feat_push(&utr[c], iv);              /* features.rs:322-326 */
+    else if (iv.isexon || iv.isgene) feat_push(&gene[c], iv);             /* features.rs:327-331 */
+  }
+  for (uint32_t c = 0; c < n_ref; ++c) { qsort(utr[c].v, utr[c].n, sizeof(feat_iv), feat_cmp); qsort(gene[c].v, gene[c].n, sizeof(feat_iv), feat_cmp); }
+  uint64_t seen = 0;
+  for (;;) { /* pass 1 driver, command.rs:291-316 */
+    int rc = read_record(rd, &rb, &rec, n_ref); if (rc < 0) return NULL; if (rc == 0) break;
+    const char* nm = (const char*)rb.buf + 32;
+    if (rec.l_name <= 1 || (rec.l_name == 2 && nm[0] == '*')) { snprintf(g_err, sizeof g_err, "Could not parse read name"); return NULL; }
+    if (rec.flag & 0x4) F->ignored_flags++;
+    else {
+      if (rec.ref_id < 0) { snprintf(g_err, sizeof g_err, "Could not parse reference sequence id for read"); return NULL; }
+      if (!refs[rec.ref_id].primary) F->ignored_nonprimary++;
+      else {
+        if (rec.pos < 0) { snprintf(g_err, sizeof g_err, "Could not parse record's start position."); return NULL; }
+        const uint64_t start = (uint64_t)rec.pos + 1, end = start + rec.span, qstop = end + 1;
+        int c5 = 0, c3 = 0, cc = 0;
+        const feat_list* U = &utr[rec.ref_id];
+        for (size_t i = 0; i < U->n && U->v[i].start < qstop; ++i) { /* features.rs:185-209, in Lapper order */
+          const feat_iv* iv = &U->v[i];
+          if (!(iv->stop > start)) continue;
+          if (!c5 && iv->is5) { c5 = 1; F->utr5++; }
+          else if (!c3 && iv->is3) { c3 = 1; F->utr3++; }
+          else if (!cc && iv->iscds) { cc = 1; F->cds++; }
+        }
+        int has_gene = 0, has_exon = 0;
+        const feat_list* G = &gene[rec.ref_id];
+        for (size_t i = 0; i < G->n && G->v[i].start < qstop; ++i) { /* features.rs:212-226 */
+          const feat_iv* iv = &G->v[i];
+          if (!(iv->stop > start)) continue;
+          if (iv->isgene) has_gene = 1; else if (iv->isexon) has_exon = 1;
+          if (has_gene && has_exon) break;
+        }
+        if (has_gene) { if (has_exon) F->exonic++; else F->intronic++; } else F->intergenic++; /* features.rs:228-236 */
+        F->processed++;
+      }
+    }
+    if (n_records && ++seen >= n_records) break;
+  }
+  const double tot = (double)(F->ignored_flags + F->ignored_nonprimary + F->processed); /* features.rs:244-259: 0/0 = NaN -> JSON null */
+  F->ignored_flags_pct = (double)F->ignored_flags / tot * 100.0;
+  F->ignored_nonprimary_pct = (double)F->ignored_nonprimary / tot * 100.0;
+  free(rd); free(rb.buf);
+  return F;
+}
+/* counts: utr_five_prime, utr_three_prime, coding_sequence, intergenic, exonic, intronic, processed, ignored_flags,
+ * ignored_nonprimary_chromosome (field order of features/metrics.rs) */
+void oracle_features_get(void* p, uint64_t counts[9], double pct[2]) {
+  features_t* F = p;
+  counts[0] = F->utr5; counts[1] = F->utr3; counts[2] = F->cds; counts[3] = F->intergenic; counts[4] = F->exonic; counts[5] = F->intronic;
+  counts[6] = F->processed; counts[7] = F->ignored_flags; counts[8] = F->ignored_nonprimary;
+  pct[0] = F->ignored_flags_pct; pct[1] = F->ignored_nonprimary_pct;
+}
+
 #ifdef ORACLE_MAIN
 static uint8_t* slurp(const char* path, size_t* n) {
   FILE* f = fopen(path, "rb"); if (!f) return NULL;
