@@ -21,7 +21,11 @@
 namespace ngsq {
 
 constexpr int kDecBatch = 32;  // symbols per lane between header / overrun checks
+#if NGSQ_DEC_VARIANT & 8
+constexpr int kDecWarps = 18;  // 18 x 32 x 396 B of slabs (+ 256 B of static shared memory with variant 1)
+#else
 constexpr int kDecWarps = (227 * 1024 / kSlabBytes) / 32 > 17 ? 17 : (227 * 1024 / kSlabBytes) / 32;  // 17 x 32 x 420 B of slabs; 120 registers per thread
+#endif
 constexpr int kDecThreads = kDecWarps * 32;
 constexpr size_t kDecSmem = (size_t)kDecThreads * kSlabBytes;
 
@@ -33,6 +37,12 @@ inflate_decode_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
   Lane L;
   L.slab = smem_raw + (size_t)threadIdx.x * kSlabBytes;
   L.state = LS_IDLE;
+#if NGSQ_DEC_VARIANT & 1
+  __shared__ uint32_t s_base_lut[64];
+  if (threadIdx.x < 64) s_base_lut[threadIdx.x] = base_lut_entry(threadIdx.x);
+  __syncthreads();
+  L.lut = s_base_lut;
+#endif
   for (;;) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(queue, 32u);

@@ -46,8 +46,32 @@
 
 namespace ngsq {
 
+// Symbol-loop variants prepared for measurement (bit mask; build with -DNGSQ_DEC_VARIANT=n).
+// The default build (0) is the measured and GPU-verified kernel; every variant decodes bit-identically in the host
+// model (tests/test_inflate_model.py) but has not run on a GPU yet.
+//   1  length / distance bases and extra-bit counts from a 64-word table (per-CTA shared memory) instead of arithmetic
+//   2  match bitmap word flushed by a predicated store instead of a branch
+//   4  emit(): chunk stores predicated, accumulator updates by selects (no divergent flush paths, no phi copies)
+//   8  396-byte slab (u8 distance bases, exact-size symbol arrays): 18 decoder warps per SM instead of 17
+//  16  code length = 1 - (signed byte dot product of the sign-replicated flag bytes): 4 PRMT + 4 IDP.4A instead of
+//      4 PRMT + 7 logic ops + POPC, twice per match
+#ifndef NGSQ_DEC_VARIANT
+#define NGSQ_DEC_VARIANT 0
+#endif
+
+#if NGSQ_DEC_VARIANT & 8
+// ll_bt[15] and d_base[15] are indexed by length - 1 (length 16 = invalid code reads the neighbouring bytes of the
+// slab; the block is failed anyway), distance bases are kept mod 32 in bytes: 60 + 288 + 15 + 32 = 395 -> 99 words
+constexpr int SL_LLBT = 0, SL_LLS = 60, SL_DB = 348, SL_DS = 363;
+constexpr int kSlabBytes = 396;
+constexpr int kLenIndexBias = 1;
+typedef uint8_t dbase_t;
+#else
 constexpr int SL_LLS = 0, SL_LLBT = 288, SL_DS = 352, SL_DB = 384;
 constexpr int kSlabBytes = 416 + 4;
+constexpr int kLenIndexBias = 0;
+typedef int16_t dbase_t;
+#endif
 constexpr uint32_t kBitmapWords = 2048;  // per BGZF block: one bit per inflated byte (<= 65536)
 
 enum : uint32_t { kBlkOk = 0, kBlkBadStream = 1, kBlkIsize = 2, kBlkOverrun = 3 };
@@ -69,6 +93,47 @@ NGSQ_HD uint32_t brev32(uint32_t x) {
   x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
   x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
   return (x >> 16) | (x << 16);
+#endif
+}
+
+// variant 1: entry i < 32: length symbol 257 + i -> (match length - 3 base) | extra bits << 8;
+// entry 32 + i: distance symbol i -> (distance - 1 base) | extra bits << 16
+NGSQ_HD uint32_t base_lut_entry(uint32_t i) {
+  if (i < 32) {
+    const uint32_t li = i > 28 ? 28 : i;
+    const uint32_t eb = (li < 8 || li == 28) ? 0 : (li - 4) >> 2;
+    const uint32_t b = li < 8 ? li : li == 28 ? 255 : (4 + (li & 3)) << eb;
+    return b | (eb << 8);
+  }
+  const uint32_t ds = (i - 32) > 29 ? 29 : (i - 32);
+  const uint32_t deb = ds < 4 ? 0 : (ds >> 1) - 1;
+  const uint32_t b = ds < 4 ? ds : (2 + (ds & 1)) << deb;
+  return b | (deb << 16);
+}
+
+NGSQ_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {  // PRMT, default mode (selector bit 3: replicate the sign)
+#if defined(__CUDA_ARCH__)
+  uint32_t r;  // not __byte_perm(): the intrinsic masks each selector nibble to 3 bits and drops the sign mode
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+#else
+  const uint64_t v = (uint64_t)a | ((uint64_t)b << 32);
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t n = (sel >> (4 * i)) & 15;
+    uint32_t byte = (uint32_t)(v >> (8 * (n & 7))) & 255;
+    if (n & 8) byte = (byte & 128) ? 255 : 0;
+    r |= byte << (8 * i);
+  }
+  return r;
+#endif
+}
+NGSQ_HD int dp4a_s8(uint32_t a, uint32_t b, int c) {  // IDP.4A, signed bytes
+#if defined(__CUDA_ARCH__)
+  return __dp4a((int)a, (int)b, c);
+#else
+  for (int i = 0; i < 4; ++i) c += (int)(int8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i));
+  return c;
 #endif
 }
 
@@ -115,6 +180,9 @@ struct Lane {
   // canonical-code limits: llim[i] = lim[2i] | lim[2i+1] << 16, lim[0] = 0x8000 (never reached)
   uint32_t llim[8], dlim[8];
   uint8_t* slab;            // shared memory (host model: heap)
+#if NGSQ_DEC_VARIANT & 1
+  const uint32_t* lut;      // base_lut_entry(0..63)
+#endif
   uint32_t err;
   int state;
   bool bfinal;
@@ -123,9 +191,9 @@ struct Lane {
 #endif
 
   NGSQ_HD uint8_t* ll_sorted() const { return slab + SL_LLS; }
-  NGSQ_HD uint32_t* ll_bt() const { return reinterpret_cast<uint32_t*>(slab + SL_LLBT); }
+  NGSQ_HD uint32_t* ll_bt() const { return reinterpret_cast<uint32_t*>(slab + SL_LLBT) - kLenIndexBias; }  // index: code length
   NGSQ_HD uint8_t* d_sorted() const { return slab + SL_DS; }
-  NGSQ_HD int16_t* d_base() const { return reinterpret_cast<int16_t*>(slab + SL_DB); }
+  NGSQ_HD dbase_t* d_base() const { return reinterpret_cast<dbase_t*>(slab + SL_DB) - kLenIndexBias; }
 
   // ---------------- bit reader ----------------
   static NGSQ_HD void ld64(const uint8_t* p, uint32_t& lo, uint32_t& hi) {  // p is 8-byte aligned
@@ -260,6 +328,63 @@ struct Lane {
     }
     bm |= 1u << (p & 31);
   }
+  // ---- variants 2 / 4: stores under a predicate instead of a branch (device: one @p ST; host: an if) ----
+  static NGSQ_HD void store16_if(bool c, uint8_t* p, uint64_t lo, uint64_t hi) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.v4.u32 [%1], {%2, %3, %4, %5};\n\t}"
+                 :: "r"((uint32_t)c), "l"(p), "r"((uint32_t)lo), "r"((uint32_t)(lo >> 32)), "r"((uint32_t)hi), "r"((uint32_t)(hi >> 32)) : "memory");
+#else
+    if (c) { memcpy(p, &lo, 8); memcpy(p + 8, &hi, 8); }
+#endif
+  }
+  static NGSQ_HD void store4_if(bool c, uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}" :: "r"((uint32_t)c), "l"(p), "r"(v) : "memory");
+#else
+    if (c) *p = v;
+#endif
+  }
+  NGSQ_HD void flush_chunk_if(bool c, uint32_t cq) {
+    const bool inner = cq >= q0 && cq + 16 <= qend;
+    store16_if(c && inner, obase + cq, acc_lo, acc_hi);
+    if (c && !inner) flush_edge(obase, q0, qend, acc_lo, acc_hi, cq);  // first / last chunk of the block only
+#ifdef NGSQ_HOST_MODEL
+    if (ctr && c) { if (inner) ctr->chunk_stores++; else ctr->edge_stores++; }
+#endif
+  }
+  NGSQ_HD void emit_sel(uint32_t v, uint32_t n, uint32_t sk) {  // same contract as emit()
+    const uint32_t pos = q & 15;
+    const uint32_t s = pos * 8;
+    const uint64_t V = v;
+    const bool in_lo = s < 64;
+    const uint32_t s6 = s & 63;
+    const uint64_t up = V << s6;
+    const uint64_t carry = (V >> 1) >> (63 - s6);
+    acc_lo |= in_lo ? up : 0;
+    acc_hi |= in_lo ? carry : up;
+    const uint32_t nq = q + n;
+    const bool cross1 = ((nq ^ q) & 16) != 0;  // the token completes this chunk
+    flush_chunk_if(cross1, q & ~15u);
+    // bytes of the token that spill into the next chunk: 16 - pos is 1..3 whenever cross1 holds (n <= 3),
+    // and the shifted-out value is 0 when the token ends exactly at the boundary
+    const uint32_t left = v >> ((8 * (16 - pos)) & 31);
+    acc_lo = cross1 ? (uint64_t)left : acc_lo;
+    acc_hi = cross1 ? 0 : acc_hi;
+    const uint32_t sq = nq + sk;
+    const bool cross2 = (sq >> 4) != (nq >> 4);  // the match bytes left to the resolve kernel leave the chunk
+    flush_chunk_if(cross2 && (nq & 15), nq & ~15u);
+    acc_lo = cross2 ? 0 : acc_lo;
+    acc_hi = cross2 ? 0 : acc_hi;
+    q = sq;
+  }
+  NGSQ_HD void mark_match_if(bool ok, uint32_t p) {
+    const uint32_t w = p >> 5;
+    const bool nw = ok && w != bm_w;
+    store4_if(nw && bm != 0, bitmap + bm_w, bm);
+    bm = nw ? 0 : bm;
+    bm_w = nw ? w : bm_w;
+    bm |= ok ? 1u << (p & 31) : 0u;
+  }
   NGSQ_HD void finish_output() {
     if (q & 15) flush_chunk(q & ~15u);
     acc_lo = 0;
@@ -298,7 +423,7 @@ struct Lane {
   // packed limits.  Literal/length table: bt32 != nullptr and `split` = 256 (the index of the first
   // symbol >= split of each length goes into the high half of bt32[]); distance table: base16.
   template <class LenFn>
-  NGSQ_HD bool build(LenFn lens, uint32_t n, uint8_t* sorted, uint32_t* lim_packed, uint32_t* bt32, int16_t* base16, uint32_t split,
+  NGSQ_HD bool build(LenFn lens, uint32_t n, uint8_t* sorted, uint32_t* lim_packed, uint32_t* bt32, dbase_t* base16, uint32_t split,
                      uint16_t* nx /* scratch[16] */) {
     for (int i = 0; i < 16; ++i) nx[i] = 0;
     for (uint32_t k = 0; k < n; ++k) nx[lens(k)]++;
@@ -315,7 +440,7 @@ struct Lane {
       const uint32_t lim = (code + c) << (15 - l);  // <= 0x8000
       if (l & 1) lim_packed[l >> 1] = lim_lo | (lim << 16); else lim_lo = lim;
       const int b = (int)off - (int)code;
-      if (bt32) bt32[l] = ((uint32_t)b & 0xFFFFu) | (off << 16); else base16[l] = (int16_t)b;
+      if (bt32) bt32[l] = ((uint32_t)b & 0xFFFFu) | (off << 16); else base16[l] = (dbase_t)b;  // used mod 32
       nx[l] = (uint16_t)off;  // running index of the next symbol of this length
       off += c;
     }
@@ -333,7 +458,17 @@ struct Lane {
   // code length of the next symbol: 1 + number of limits the next 15 bits (MSB first) reach
   static NGSQ_HD uint32_t code_len(uint32_t x, const uint32_t* lim_packed) {
     const uint32_t x2 = (x * 0x10001u) | 0x80008000u;
-#if defined(__CUDA_ARCH__)
+#if NGSQ_DEC_VARIANT & 16
+    // bytes 1 and 3 of (x2 - lim) carry the "x >= lim" flags in their top bits: replicate them to 0x00 / 0xFF
+    // (= 0 / -1 as signed bytes) and add the sixteen of them up with four dot products
+    const uint32_t h0 = byte_perm(x2 - lim_packed[0], x2 - lim_packed[1], 0xFDB9);
+    const uint32_t h1 = byte_perm(x2 - lim_packed[2], x2 - lim_packed[3], 0xFDB9);
+    const uint32_t h2 = byte_perm(x2 - lim_packed[4], x2 - lim_packed[5], 0xFDB9);
+    const uint32_t h3 = byte_perm(x2 - lim_packed[6], x2 - lim_packed[7], 0xFDB9);
+    const int c01 = dp4a_s8(h1, 0x01010101u, dp4a_s8(h0, 0x01010101u, -1));  // -1 - (limits 0..7 reached)
+    const int c23 = dp4a_s8(h3, 0x01010101u, dp4a_s8(h2, 0x01010101u, 0));   // -(limits 8..15 reached)
+    return (uint32_t)(0 - c01 - c23);
+#elif defined(__CUDA_ARCH__)
     // bit 15 of each half of (x2 - lim) says x >= lim: gather the 16 flag bytes with four byte
     // permutes, interleave their top bits into one word, popcount
     const uint32_t g0 = __byte_perm(x2 - lim_packed[0], x2 - lim_packed[1], 0x7531);
@@ -481,7 +616,11 @@ struct Lane {
     const uint32_t x = brev32(peek()) >> 17;
     const uint32_t len = code_len(x, llim);             // 1..15, 16 = bits beyond an incomplete code
     uint32_t bad_stream = len >> 4, overrun = 0;
+#if NGSQ_DEC_VARIANT & 8
+    const uint32_t bt = ll_bt()[len];  // 1..16
+#else
     const uint32_t bt = ll_bt()[len & 15];
+#endif
     const uint32_t idx = ((x >> ((15 - len) & 31)) + bt) & 0xFFFFu;  // index into sorted (the base is kept mod 2^16)
     const uint32_t s8 = ll_sorted()[idx < 288 ? idx : 0];
     const bool upper = idx >= (bt >> 16);  // symbol >= 256
@@ -499,6 +638,10 @@ struct Lane {
       // length symbol 257 + li: li < 8: 3 + li;  li = 28: 258;  else 3 + ((4 + (li & 3)) << eb) + extra, eb = (li - 4) >> 2
       const uint32_t li = s8 - 1;
       bad_stream |= li > 28;
+#if NGSQ_DEC_VARIANT & 1
+      const uint32_t le = lut[li & 31];
+      const uint32_t mlen = 3 + (le & 255) + take(le >> 8);
+#else
       const uint32_t lc = li > 28 ? 28 : li;
       uint32_t eb = ((lc < 4 ? 4 : lc) - 4) >> 2;
       uint32_t lbase = (4 + (lc & 3)) << eb;
@@ -506,10 +649,15 @@ struct Lane {
       lbase = lc == 28 ? 255 : lbase;
       eb = lc == 28 ? 0 : eb;
       const uint32_t mlen = 3 + lbase + take(eb);
+#endif
       const uint32_t dx = brev32(peek()) >> 17;
       const uint32_t dl = code_len(dx, dlim);
       bad_stream |= dl >> 4;
+#if NGSQ_DEC_VARIANT & 8
+      const uint32_t di = ((dx >> ((15 - dl) & 31)) + (uint32_t)d_base()[dl]) & 31u;
+#else
       const uint32_t di = ((dx >> ((15 - dl) & 31)) + (uint32_t)(int)d_base()[dl & 15]) & 31u;
+#endif
       const uint32_t ds = d_sorted()[di];
       bad_stream |= ds > 29;
       drop(dl);
@@ -517,14 +665,23 @@ struct Lane {
       if (ctr) ctr->d_len_hist[dl]++;
 #endif
       // distance symbol ds: ds < 4: 1 + ds;  else 1 + ((2 + (ds & 1)) << deb) + extra, deb = (ds >> 1) - 1
+#if NGSQ_DEC_VARIANT & 1
+      const uint32_t de = lut[32 + (ds & 31)];
+      const uint32_t dist = 1 + (de & 0xFFFFu) + take(de >> 16);
+#else
       const uint32_t dc = ds > 29 ? 29 : ds;
       const uint32_t deb = ((dc >> 1) < 1 ? 1 : (dc >> 1)) - 1;
       uint32_t dbase = 1 + ((2 + (dc & 1)) << deb);
       dbase = dc < 2 ? dc + 1 : dbase;
       const uint32_t dist = dbase + take(deb);
+#endif
       const uint32_t p = q - q0;
       overrun |= (dist > p) | (q + mlen > qend);
+#if NGSQ_DEC_VARIANT & 2
+      mark_match_if(!(bad_stream | overrun), p);
+#else
       if (!(bad_stream | overrun)) mark_match(p);
+#endif
       v = (mlen - 3) | ((dist - 1) << 8);
       n = 3;
       sk = mlen - 3;
@@ -538,7 +695,11 @@ struct Lane {
 #endif
     }
     if (bad_stream | overrun) { end_block(bad_stream ? kBlkBadStream : kBlkOverrun); return; }
+#if NGSQ_DEC_VARIANT & 4
+    emit_sel(v, n, sk);
+#else
     emit(v, n, sk);
+#endif
   }
 };
 

@@ -17,11 +17,13 @@ from bamutil import bgzf_block
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def model(tmp_path_factory):
+# 0 = the shipped decoder; the others are the symbol-loop variants prepared for measurement
+# (NGSQ_DEC_VARIANT in inflate_lane.cuh): each bit alone and all together must decode identically
+@pytest.fixture(scope="module", params=[0, 1, 2, 4, 8, 16, 31], ids=lambda v: f"variant{v}")
+def model(request, tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("model") / "inflate_model")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-DNGSQ_HOST_MODEL", "-Wno-unknown-pragmas", "-o", exe,
-                    os.path.join(ROOT, "tools", "inflate_model.cpp"), "-lz"], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-DNGSQ_HOST_MODEL", f"-DNGSQ_DEC_VARIANT={request.param}", "-Wno-unknown-pragmas",
+                    "-I", os.path.join(ROOT, "ngs_b200", "csrc"), "-o", exe, os.path.join(ROOT, "tools", "inflate_model.cpp"), "-lz"], check=True)
     return exe
 
 

@@ -103,6 +103,10 @@ int main(int argc, char** argv) {
   uint64_t fuzz_runs = 0, fuzz_failed = 0, fuzz_ok = 0, rng = 0x9E3779B97F4A7C15ull;
 
   InflateCounters ctr;
+#if NGSQ_DEC_VARIANT & 1
+  static uint32_t base_lut[64];
+  for (uint32_t i = 0; i < 64; ++i) base_lut[i] = base_lut_entry(i);
+#endif
   std::vector<uint8_t> slab(kSlabBytes);
 
   std::vector<uint32_t> bitmap(kBitmapWords);
@@ -140,6 +144,9 @@ int main(int argc, char** argv) {
       memset(bitmap.data(), 0, kBitmapWords * 4);
       Lane L;
       L.slab = slab.data();
+#if NGSQ_DEC_VARIANT & 1
+      L.lut = base_lut;
+#endif
       L.ctr = nullptr;
       L.begin_block(d, out.data(), bitmap.data());
       uint64_t steps = 0;
@@ -181,6 +188,9 @@ int main(int argc, char** argv) {
         memset(bitmap.data(), 0, kBitmapWords * 4);
         Lane L;
         L.slab = slab.data();
+#if NGSQ_DEC_VARIANT & 1
+      L.lut = base_lut;
+#endif
 
         L.ctr = mis == 0 ? &ctr : nullptr;
         L.begin_block(d, out.data(), bitmap.data());
