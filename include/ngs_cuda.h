@@ -131,7 +131,9 @@ int ngsq_bgzf_walk(const uint8_t* bgzf, size_t nbytes, uint64_t file_off, ngsq_b
  * ngsq_finish returns.  Chunks must be submitted in file order. */
 int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t file_off);
 /* Same for a chunk already resident in DEVICE memory (used in place, not copied); the caller
- * passes the descriptors ngsq_bgzf_walk produced for it. */
+ * passes the descriptors ngsq_bgzf_walk produced for it.  The allocation must stay readable for 64 bytes
+ * past nbytes: the decoders read their input through aligned 8-byte windows that run ahead of the last
+ * block's end (ngsq_submit pads its own copies). */
 int ngsq_submit_device(ngsq_engine* e, const void* dev_bgzf, size_t nbytes, const ngsq_block* blocks, uint32_t n_blocks);
 
 /* Record-boundary scan, facet kernels, coverage resolve; blocks until the device is done. */

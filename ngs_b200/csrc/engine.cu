@@ -292,7 +292,14 @@ int inflate_new_blocks(ngsq_engine* e, uint32_t first_new, uint32_t n_new) {
       uint32_t* ns = nullptr;
       CU(cudaMalloc(&ns, cap * 4));
       CU(cudaMemsetAsync(ns, 0, cap * 4, e->s_comp));
-      if (e->d_status) { CU(cudaStreamSynchronize(e->s_comp)); CU(cudaStreamSynchronize(e->s_aux)); cudaFree(e->d_status); }
+      if (e->d_status) {
+        // the verdicts of the blocks decoded so far move along (same stream as the launches that wrote them):
+        // ngsq_finish reports a failed block whichever launch it was in
+        if (first_new) CU(cudaMemcpyAsync(ns, e->d_status, (size_t)first_new * 4, cudaMemcpyDeviceToDevice, e->s_comp));
+        CU(cudaStreamSynchronize(e->s_comp));
+        CU(cudaStreamSynchronize(e->s_aux));
+        cudaFree(e->d_status);
+      }
       e->d_status = ns;
     }
     if (cap > e->crcx_cap) {  // expected CRC32 per block (trailer values), checked right after each launch
