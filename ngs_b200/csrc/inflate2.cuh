@@ -66,6 +66,14 @@ inflate_decode_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
   }
 }
 
+// Resolve variants prepared for measurement (bit mask, -DNGSQ_RES_VARIANT=n; 0 = the measured, shipped kernel):
+//   1  dependency masks from the bitmap's ranks (two popcounts over the super-window's bitmap words + one look at the
+//      preceding token) instead of two 6-step binary searches by shuffle: 2 shared-memory loads + 1 shuffle instead of 12 shuffles, the same masks
+//      (tools/inflate_model.cpp checks the equality on every batch)
+#ifndef NGSQ_RES_VARIANT
+#define NGSQ_RES_VARIANT 0
+#endif
+
 constexpr int kResThreads = 256;
 constexpr int kResWarps = kResThreads / 32;
 constexpr int kResList = 352;  // matches that can start inside 1024 bytes (every match is >= 3 bytes)
@@ -108,6 +116,9 @@ __global__ void __launch_bounds__(kResThreads)
 inflate_resolve_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ blocks, uint32_t n_blocks,
                        const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ status) {
   __shared__ uint16_t s_pos[kResWarps][kResList];
+#if NGSQ_RES_VARIANT & 1
+  __shared__ uint2 s_rank[kResWarps][32];
+#endif
   const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const uint32_t n_warps = gridDim.x * kResWarps;
   uint16_t* list = s_pos[wic];
@@ -129,6 +140,11 @@ inflate_resolve_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ 
       const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
       if (!total) continue;
       uint32_t o = incl - cnt;
+#if NGSQ_RES_VARIANT & 1
+      // entry w: bitmap word w of this super-window and the number of matches that start before it (shared memory
+      // rather than shuffles: the kernel runs at 32 registers per thread for full occupancy)
+      s_rank[wic][lane] = make_uint2(word, o);
+#endif
       const uint32_t pbase = (sw << 10) + (lane << 5);
       while (word) {
         const uint32_t bit = __ffs(word) - 1;
@@ -158,7 +174,22 @@ inflate_resolve_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ 
         const uint32_t dpos = active ? pos : 0x20000u, dend = active ? pos + mlen : 0x20000u;
         const uint32_t s_lo = pos - dist, s_hi = s_lo + min(mlen, dist);  // source bytes [s_lo, s_hi)
         // earlier lanes whose destination overlaps my source: lanes [lo, hi) with
-        //   lo = first lane with dend > s_lo,  hi = first lane with dpos >= s_hi   (binary search by shuffle)
+        //   lo = first lane with dend > s_lo,  hi = first lane with dpos >= s_hi
+#if NGSQ_RES_VARIANT & 1
+        // rank(x) = matches of this super-window that start before window-relative byte x: the matches that start inside
+        // my source are the list entries [rank(s_lo), rank(s_hi)); the one before them counts if it reaches past s_lo.
+        // Matches of earlier batches and earlier super-windows are resolved already.
+        const uint32_t W = sw << 10;
+        const uint32_t x_lo = min(max(s_lo, W) - W, 1023u), x_hi = min(max(s_hi, W) - W, 1023u);
+        const uint2 e_lo = s_rank[wic][x_lo >> 5], e_hi = s_rank[wic][x_hi >> 5];
+        const uint32_t r_lo = e_lo.y + __popc(e_lo.x & ((1u << (x_lo & 31)) - 1u));
+        const uint32_t r_hi = e_hi.y + __popc(e_hi.x & ((1u << (x_hi & 31)) - 1u));
+        const int pl = (int)r_lo - 1 - (int)base;  // lane of the match before my source, if it is in this batch
+        const uint32_t prev_end = __shfl_sync(0xFFFFFFFFu, dend, pl & 31);
+        const int lo = max((int)r_lo - (int)base - ((pl >= 0 && prev_end > s_lo) ? 1 : 0), 0), hi = (int)r_hi - (int)base;
+        uint32_t dep = 0;
+        if (active && hi > lo) dep = ((1u << hi) - 1u) & ~((1u << lo) - 1u) & ((1u << lane) - 1u);  // hi <= lane
+#else
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int step = 32; step; step >>= 1) {
@@ -170,6 +201,7 @@ inflate_resolve_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ 
         }
         uint32_t dep = 0;
         if (active && hi > lo) dep = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u) & ((1u << lane) - 1u);
+#endif
         uint32_t done = __ballot_sync(0xFFFFFFFFu, !active);
         while (done != 0xFFFFFFFFu) {
           const bool ready = !((done >> lane) & 1u) && (dep & ~done) == 0;

@@ -69,6 +69,23 @@ static void resolve_block_model(uint8_t* ob, uint32_t isize, const uint32_t* bit
         }
         dep[l] = 0;
         if (active[l] && hi > lo) dep[l] = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u) & ((1u << l) - 1u);
+        // the rank formulation of NGSQ_RES_VARIANT 1 (inflate2.cuh) must give the same mask
+        {
+          const uint32_t W = sw << 10;
+          const uint32_t x_lo = std::min(std::max(s_lo[l], W) - W, 1023u), x_hi = std::min(std::max(s_hi[l], W) - W, 1023u);
+          auto rank = [&](uint32_t x) {
+            uint32_t excl = 0;
+            for (uint32_t w = 0; w < (x >> 5); ++w) excl += (uint32_t)__builtin_popcount(bitmap[sw * 32 + w]);
+            return excl + (uint32_t)__builtin_popcount(bitmap[sw * 32 + (x >> 5)] & ((1u << (x & 31)) - 1u));
+          };
+          const uint32_t r_lo = rank(x_lo), r_hi = rank(x_hi);
+          const int pl = (int)r_lo - 1 - (int)base;
+          const uint32_t prev_end = dend[pl & 31];
+          const int lo2 = std::max((int)r_lo - (int)base - ((pl >= 0 && prev_end > s_lo[l]) ? 1 : 0), 0), hi2 = (int)r_hi - (int)base;
+          uint32_t dep2 = 0;
+          if (active[l] && hi2 > lo2) dep2 = ((1u << hi2) - 1u) & ~((1u << lo2) - 1u) & ((1u << l) - 1u);
+          if (dep2 != dep[l]) { fprintf(stderr, "resolve model: rank-based mask %08x != searched mask %08x (lane %u)\n", dep2, dep[l], l); exit(1); }
+        }
       }
       uint32_t done = 0;
       for (uint32_t l = 0; l < 32; ++l) if (!active[l]) done |= 1u << l;
