@@ -51,13 +51,16 @@ enum {
   NGSQ_E_QUAL_RANGE = -7, /* quality score > 93 (the reference's decoder aborts the run) */
   NGSQ_E_CHAIN = -8,      /* record-boundary closure check failed */
   NGSQ_E_NCCL = -9,
-  NGSQ_E_NOMEM = -10
+  NGSQ_E_NOMEM = -10,
+  NGSQ_E_EDITS = -11      /* the Edits facet met a record / reference the reference program aborts on */
 };
 
 /* ngsq_config.flags */
 #define NGSQ_F_RECORD_FACETS 1u /* General, Template Length, GC Content, Quality Score */
 #define NGSQ_F_COVERAGE 2u      /* Coverage */
 #define NGSQ_F_VERIFY_CRC 4u    /* verify the CRC32 of every block (reference behaviour) */
+#define NGSQ_F_EDITS 8u         /* Edits (needs ngsq_set_reference_bases for every contig that holds records);
+                                   written against the oracle and a host model, not yet measured on a GPU */
 
 typedef struct ngsq_engine ngsq_engine;
 
@@ -98,6 +101,7 @@ typedef struct ngsq_stats {
   float ms_inflate_decode;   /* of ms_inflate: the lane-per-block Huffman decode kernel */
   float ms_inflate_resolve;  /* of ms_inflate: the warp-per-block LZ77 resolve kernel */
   float ms_reduce;           /* ngsq_reduce: agreement all-reduce + sum-reduce + refresh (0 without it) */
+  float ms_edits;            /* Edits kernel + VAF histogram (0 without NGSQ_F_EDITS) */
 } ngsq_stats;
 
 int ngsq_version(void);
@@ -112,6 +116,13 @@ int ngsq_reset(ngsq_engine* e);
  * processes it (CoverageFacet::supports_sequence_name, coverage.rs:133-138 — decided by the
  * caller from the genome's primary-assembly table).  Must precede the first submit. */
 int ngsq_set_references(ngsq_engine* e, uint32_t n_ref, const uint32_t* ref_len, const uint8_t* coverage_enabled);
+
+/* Edits facet (src/qc/sequence_based/edits.rs:175-215, setup): the letters of reference `ref`'s sequence from the
+ * reference FASTA, line ends removed, as they stand in the file (the engine applies noodles' Base::try_from rule:
+ * the sixteen upper-case letters "=ACMGRSVTWYHKDBN"; a record over any other letter fails the run as it does in the
+ * reference).  After ngsq_set_references, before the first submit; the caller reports "sequence not found" itself
+ * for contigs the FASTA lacks (a record on a contig without a sequence fails the run).  Needs NGSQ_F_EDITS. */
+int ngsq_set_reference_bases(ngsq_engine* e, uint32_t ref, const uint8_t* letters, uint64_t n);
 
 /* Virtual offsets (coffset << 16 | uoffset) of the first record this shard owns and of the
  * first record it does NOT own (0 = everything to the end of the submitted data).  Both must
@@ -162,6 +173,10 @@ typedef struct ngsq_cov_ints {
 /* bin_sums[k] = sum of depth over the k-th bin of coverage.rs:206-230 (bin 0 = position 0). */
 int ngsq_get_coverage_contig(ngsq_engine* e, uint32_t ref, ngsq_cov_ints* out, uint64_t* bin_sums, size_t cap);
 int ngsq_get_coverage_global(ngsq_engine* e, uint64_t* nonsensical_records);
+/* Edits (edits.rs:22-46): the integer state of EditMetrics when aggregate() runs — read_one_edits / read_two_edits
+ * (Histogram 0..=512 of edits per read), vaf_histogram (0..=100, filled by teardown, edits.rs:318-334) and the number
+ * of records that were stepped through.  The two means of the summary are the caller's (Histogram::mean). */
+int ngsq_get_edits(ngsq_engine* e, uint64_t read_one[513], uint64_t read_two[513], uint64_t vaf[101], uint64_t* records);
 int ngsq_get_stats(ngsq_engine* e, ngsq_stats* out);
 
 /* ---- multi-GPU merge: one sum-reduce of the packed u64 result buffer ---- */

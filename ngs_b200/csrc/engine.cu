@@ -20,6 +20,7 @@
 #include "../../include/ngs_cuda.h"
 #include "coverage.cuh"
 #include "crc32.cuh"
+#include "edits.cuh"
 #include "facets.cuh"
 #include "inflate2.cuh"
 #include "recscan.cuh"
@@ -143,6 +144,16 @@ struct ngsq_engine {
   ngsq_stats stats{};
   uint32_t other_launches = 0;
 
+  // Edits facet (NGSQ_F_EDITS): per-contig FASTA codes, per-position counters, result block
+  std::vector<EditsContig> ed_contigs;
+  std::vector<void*> ed_allocs;          // device allocations behind ed_contigs
+  EditsContig* d_ed_contigs = nullptr;
+  uint32_t *d_ed_refs = nullptr, *d_ed_alts = nullptr;
+  uint64_t ed_pos_total = 0;
+  unsigned long long* d_ed_res = nullptr;
+  std::vector<uint64_t> h_ed_res;
+  cudaEvent_t ev_g = nullptr;
+
   // nccl
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -214,6 +225,13 @@ int start_run(ngsq_engine* e) {
   if ((e->cfg.flags & NGSQ_F_COVERAGE) && e->diff_elems) CU(cudaMemsetAsync(e->d_diff, 0, e->diff_elems * 4, e->s_comp));
   CU(cudaMemsetAsync(e->d_queue, 0, ngsq_engine::kQueueSlots * 4, e->s_comp));
   CU(cudaMemsetAsync(e->d_flags, 0, sizeof(DevFlags), e->s_comp));
+  if ((e->cfg.flags & NGSQ_F_EDITS) && e->d_ed_res) {
+    CU(cudaMemsetAsync(e->d_ed_res, 0, E_WORDS * 8, e->s_comp));
+    if (e->ed_pos_total) {
+      CU(cudaMemsetAsync(e->d_ed_refs, 0, e->ed_pos_total * 4, e->s_comp));
+      CU(cudaMemsetAsync(e->d_ed_alts, 0, e->ed_pos_total * 4, e->s_comp));
+    }
+  }
   e->run_started = true;
   return NGSQ_OK;
 }
@@ -425,7 +443,7 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   CUC(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&e->s_aux, cudaStreamNonBlocking));
-  for (cudaEvent_t* ev : {&e->ev_start, &e->ev_a, &e->ev_b, &e->ev_c, &e->ev_d, &e->ev_e, &e->ev_f}) CUC(cudaEventCreate(ev));
+  for (cudaEvent_t* ev : {&e->ev_start, &e->ev_a, &e->ev_b, &e->ev_c, &e->ev_d, &e->ev_e, &e->ev_f, &e->ev_g}) CUC(cudaEventCreate(ev));
   CUC(cudaMalloc(&e->d_queue, ngsq_engine::kQueueSlots * 4));
   CUC(cudaMalloc(&e->d_flags, sizeof(DevFlags)));
   CUC(cudaMalloc(&e->d_crc_tables, sizeof(CrcTables)));
@@ -466,11 +484,13 @@ void ngsq_destroy(ngsq_engine* e) {
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto ev : e->copy_events) cudaEventDestroy(ev);
   for (auto& p : e->inflate_events) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
-  for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_c, e->ev_d, e->ev_e, e->ev_f}) if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_c, e->ev_d, e->ev_e, e->ev_f, e->ev_g}) if (ev) cudaEventDestroy(ev);
   void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_res, e->d_out,
                   e->d_blocks, e->d_status, e->d_crcx, e->d_bitmap, e->d_queue, e->d_agree, e->d_out_off, e->d_coff, e->d_base, e->d_rec, e->d_first, e->d_landed,
                   e->d_count, e->d_flags, e->d_crc_tables};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (void* p : e->ed_allocs) cudaFree(p);
+  for (void* p : {(void*)e->d_ed_contigs, (void*)e->d_ed_refs, (void*)e->d_ed_alts, (void*)e->d_ed_res}) if (p) cudaFree(p);
   for (auto& sg : e->comp_segs) cudaFree(sg.ptr);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
@@ -504,6 +524,7 @@ int ngsq_reset(ngsq_engine* e) {
   if (e->d_status && e->blocks_cap) CU(cudaMemsetAsync(e->d_status, 0, (size_t)e->blocks_cap * 4, e->s_comp));
   e->run_started = false; e->finished = false;
   e->h_res.clear(); e->h_qpos = 0;
+  e->h_ed_res.clear();
   memset(&e->stats, 0, sizeof e->stats);
   return NGSQ_OK;
 }
@@ -550,6 +571,55 @@ int ngsq_set_references(ngsq_engine* e, uint32_t n_ref, const uint32_t* ref_len,
   int rc = ensure_res(e, 256, false);
   if (rc) return rc;
   CU(cudaStreamSynchronize(e->s_comp));
+  if (e->cfg.flags & NGSQ_F_EDITS) {
+    // sequences loaded for an earlier header are dropped; per-position counters cover 0..=L of every contig
+    for (void* p : e->ed_allocs) cudaFree(p);
+    e->ed_allocs.clear();
+    for (void* p : {(void*)e->d_ed_contigs, (void*)e->d_ed_refs, (void*)e->d_ed_alts}) if (p) cudaFree(p);
+    e->d_ed_contigs = nullptr; e->d_ed_refs = nullptr; e->d_ed_alts = nullptr;
+    e->ed_contigs.assign(n_ref, EditsContig{});
+    uint64_t total = 0;
+    for (uint32_t c = 0; c < n_ref; ++c) {
+      e->ed_contigs[c].hdr_len = ref_len[c];
+      e->ed_contigs[c].pos_off = total;
+      total += (uint64_t)ref_len[c] + 1;
+    }
+    e->ed_pos_total = total;
+    CU(cudaMalloc(&e->d_ed_contigs, nr * sizeof(EditsContig)));
+    if (n_ref) CU(cudaMemcpy(e->d_ed_contigs, e->ed_contigs.data(), n_ref * sizeof(EditsContig), cudaMemcpyHostToDevice));
+    if (total) {
+      cudaError_t r1 = cudaMalloc(&e->d_ed_refs, total * 4), r2 = r1 == cudaSuccess ? cudaMalloc(&e->d_ed_alts, total * 4) : r1;
+      if (r2 != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc per-position edit counters (%llu bytes): %s", (unsigned long long)total * 8, cudaGetErrorString(r2));
+    }
+    if (!e->d_ed_res) CU(cudaMalloc(&e->d_ed_res, E_WORDS * 8));
+  }
+  return NGSQ_OK;
+}
+
+int ngsq_set_reference_bases(ngsq_engine* e, uint32_t ref, const uint8_t* letters, uint64_t n) {
+  if (!e || (!letters && n)) return fail(e, NGSQ_E_ARG, "bad reference bases");
+  if (!(e->cfg.flags & NGSQ_F_EDITS)) return fail(e, NGSQ_E_ARG, "the engine was created without NGSQ_F_EDITS");
+  if (ref >= e->n_ref || e->ed_contigs.size() != e->n_ref) return fail(e, NGSQ_E_ARG, "ngsq_set_reference_bases: reference %u is not in the header given to ngsq_set_references", ref);
+  if (e->run_started) return fail(e, NGSQ_E_ARG, "ngsq_set_reference_bases must precede the first submit");
+  if (e->ed_contigs[ref].codes) return fail(e, NGSQ_E_ARG, "reference %u already has a sequence", ref);
+  CU(cudaSetDevice(e->device));
+  const uint64_t words = n / 32 + 1;
+  std::vector<uint8_t> codes(n + 1);
+  std::vector<uint32_t> bits(words), prefix(words);
+  edits_encode(letters, n, codes.data(), bits.data(), prefix.data());
+  uint8_t* d_codes = nullptr;
+  uint32_t *d_bits = nullptr, *d_prefix = nullptr;
+  cudaError_t rc = cudaMalloc(&d_codes, n + 64);
+  if (rc == cudaSuccess) { e->ed_allocs.push_back(d_codes); rc = cudaMalloc(&d_bits, words * 4); }
+  if (rc == cudaSuccess) { e->ed_allocs.push_back(d_bits); rc = cudaMalloc(&d_prefix, words * 4); }
+  if (rc != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc reference sequence (%llu bases): %s", (unsigned long long)n, cudaGetErrorString(rc));
+  e->ed_allocs.push_back(d_prefix);
+  CU(cudaMemcpy(d_codes, codes.data(), n, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_bits, bits.data(), words * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_prefix, prefix.data(), words * 4, cudaMemcpyHostToDevice));
+  EditsContig& C = e->ed_contigs[ref];
+  C.codes = d_codes; C.bad_bits = d_bits; C.bad_prefix = d_prefix; C.code_len = n;
+  CU(cudaMemcpy(e->d_ed_contigs + ref, &C, sizeof C, cudaMemcpyHostToDevice));
   return NGSQ_OK;
 }
 
@@ -821,6 +891,26 @@ int ngsq_finish(ngsq_engine* e) {
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(e->ev_e, s));
+  // K10 (NGSQ_F_EDITS): per-record edit counts and per-position ref / alt counters, then the VAF histogram
+  const bool do_edits = (e->cfg.flags & NGSQ_F_EDITS) && e->d_ed_res && e->ed_contigs.size() == e->n_ref;
+  if (do_edits && n_rec) {
+    EditsParams EP{};
+    EP.d = e->d_out; EP.rec = e->d_rec; EP.n_rec = n_rec; EP.out_off = e->d_out_off; EP.n_ref = (int32_t)e->n_ref;
+    EP.contigs = e->d_ed_contigs; EP.refs = e->d_ed_refs; EP.alts = e->d_ed_alts; EP.res = e->d_ed_res;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n_rec + 255) / 256, (uint64_t)e->n_sm * 8);
+    edits_kernel<<<grid, 256, 0, s>>>(EP);
+    if (e->ed_pos_total) {
+      const uint32_t vgrid = (uint32_t)std::min<uint64_t>((e->ed_pos_total + 255) / 256, (uint64_t)e->n_sm * 8);
+      edits_vaf_kernel<<<vgrid, 256, 0, s>>>(e->d_ed_refs, e->d_ed_alts, e->ed_pos_total, e->d_ed_res);
+    }
+    CU(cudaGetLastError());
+    e->other_launches += 2;
+  }
+  if (do_edits) {
+    e->h_ed_res.resize(E_WORDS);
+    CU(cudaMemcpyAsync(e->h_ed_res.data(), e->d_ed_res, E_WORDS * 8, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaEventRecord(e->ev_g, s));
   // the step ends when the CRC stream is done too (its last event closes the device-timed region)
   if (!e->inflate_events.empty()) CU(cudaStreamWaitEvent(s, e->inflate_events.back().crc_end, 0));
   e->h_res.resize(e->res_words);
@@ -850,11 +940,31 @@ int ngsq_finish(ngsq_engine* e) {
   cudaEventElapsedTime(&st.ms_scan, e->ev_b, e->ev_c);
   cudaEventElapsedTime(&st.ms_facets, e->ev_c, e->ev_d);
   cudaEventElapsedTime(&st.ms_coverage, e->ev_d, e->ev_e);
+  cudaEventElapsedTime(&st.ms_edits, e->ev_e, e->ev_g);
   cudaEventElapsedTime(&st.ms_total, e->ev_start, e->ev_f);
   st.inflate_launches = e->n_launches;
   st.other_launches = e->other_launches;
   if (e->h_res[R_ERR_QUAL]) return fail(e, NGSQ_E_QUAL_RANGE, "a record holds a quality score above 93 (the reference's decoder rejects it)");
   if (e->h_res[R_ERR_RECORD]) return fail(e, NGSQ_E_BAD_RECORD, "malformed BAM record (field overrun, CIGAR op > 8, reference id out of range, or a mapped pair without reference ids)");
+  if (do_edits && e->h_ed_res[E_ERR]) {
+    static const char* const kinds[] = {"", "", "Could not parse read name", "sequence not found in reference FASTA", "record reaches past the end of the reference sequence",
+                                        "invalid base in the reference sequence", "step-through: no reference base left", "step-through: no record base left",
+                                        "step-through: reference sequence was not fully consumed", "step-through: record sequence was not fully consumed",
+                                        "more than 512 edits in one read", "matched position beyond the sequence length of the header", "invalid CIGAR operation"};
+    const uint64_t k = e->h_ed_res[E_ERR];
+    return fail(e, NGSQ_E_EDITS, "Edits: %s (the reference aborts the run here)", k < sizeof kinds / sizeof *kinds ? kinds[k] : "unknown failure");
+  }
+  return NGSQ_OK;
+}
+
+int ngsq_get_edits(ngsq_engine* e, uint64_t read_one[513], uint64_t read_two[513], uint64_t vaf[101], uint64_t* records) {
+  if (!e) return NGSQ_E_ARG;
+  if (!e->finished || e->h_ed_res.size() != E_WORDS) return fail(e, NGSQ_E_ARG, "Edits results requested before ngsq_finish or without NGSQ_F_EDITS");
+  if (e->h_ed_res[E_ERR]) return fail(e, NGSQ_E_EDITS, "the Edits facet failed; no results");
+  if (read_one) memcpy(read_one, &e->h_ed_res[E_READ_ONE], 513 * 8);
+  if (read_two) memcpy(read_two, &e->h_ed_res[E_READ_TWO], 513 * 8);
+  if (vaf) memcpy(vaf, &e->h_ed_res[E_VAF], 101 * 8);
+  if (records) *records = e->h_ed_res[E_RECORDS];
   return NGSQ_OK;
 }
 
@@ -1007,6 +1117,14 @@ int ngsq_reduce(ngsq_engine* e, int root) {
   CU(cudaMemcpyAsync(e->d_res + R_QUAL_POSITIONS, &qmax, 8, cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));
   e->other_launches += 2;
+  if ((e->cfg.flags & NGSQ_F_EDITS) && e->d_ed_res && e->h_ed_res.size() == E_WORDS) {
+    // additive like everything else: every shard owns whole contigs, so per-position counters never meet
+    rc = g_nccl.Reduce(e->d_ed_res, e->d_ed_res, E_WORDS, ncclUint64, ncclSum, root, e->comm, s);
+    if (rc) return fail(e, NGSQ_E_NCCL, "ncclReduce (edits): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    CU(cudaMemcpyAsync(e->h_ed_res.data(), e->d_ed_res, E_WORDS * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    e->other_launches += 1;
+  }
   rc = ngsq_refresh_results(e);
   if (rc) return rc;
   CU(cudaEventRecord(e->ev_b, s));

@@ -19,11 +19,12 @@ SYNTH_PATH = os.path.join(_HERE, "libngs_synth.so")
 NGSQ_F_RECORD_FACETS = 1
 NGSQ_F_COVERAGE = 2
 NGSQ_F_VERIFY_CRC = 4
+NGSQ_F_EDITS = 8
 
 ERROR_NAMES = {
     0: "NGSQ_OK", -1: "NGSQ_E_ARG", -2: "NGSQ_E_CUDA", -3: "NGSQ_E_TRUNCATED", -4: "NGSQ_E_BAD_BLOCK",
     -5: "NGSQ_E_CRC", -6: "NGSQ_E_BAD_RECORD", -7: "NGSQ_E_QUAL_RANGE", -8: "NGSQ_E_CHAIN",
-    -9: "NGSQ_E_NCCL", -10: "NGSQ_E_NOMEM",
+    -9: "NGSQ_E_NCCL", -10: "NGSQ_E_NOMEM", -11: "NGSQ_E_EDITS",
 }
 
 # every symbol include/ngs_cuda.h declares (tests check the library exports all of them)
@@ -33,6 +34,7 @@ EXPORTED = [
     "ngsq_get_tlen", "ngsq_get_gc", "ngsq_get_quality", "ngsq_get_coverage_contig", "ngsq_get_coverage_global",
     "ngsq_get_stats", "ngsq_nccl_unique_id", "ngsq_comm_init", "ngsq_reduce", "ngsq_set_quality_positions",
     "ngsq_result_buffer", "ngsq_refresh_results", "ngsq_host_alloc", "ngsq_host_free", "ngsq_inflate_to_host",
+    "ngsq_set_reference_bases", "ngsq_get_edits",
 ]
 
 
@@ -61,6 +63,7 @@ class Stats(C.Structure):
         ("max_read_len", C.c_uint64), ("ms_inflate", C.c_float), ("ms_crc", C.c_float), ("ms_scan", C.c_float),
         ("ms_facets", C.c_float), ("ms_coverage", C.c_float), ("ms_total", C.c_float), ("inflate_launches", C.c_uint32),
         ("other_launches", C.c_uint32), ("ms_inflate_decode", C.c_float), ("ms_inflate_resolve", C.c_float), ("ms_reduce", C.c_float),
+        ("ms_edits", C.c_float),
     ]
 
     def as_dict(self):
@@ -115,6 +118,8 @@ def load_library() -> C.CDLL:
     lib.ngsq_host_free.argtypes = [P]
     lib.ngsq_host_free.restype = None
     lib.ngsq_inflate_to_host.argtypes = [P, P, C.c_size_t, P, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.ngsq_set_reference_bases.argtypes = [P, C.c_uint32, P, C.c_uint64]
+    lib.ngsq_get_edits.argtypes = [P, u64p, u64p, u64p, u64p]
     _lib = lib
     return lib
 
@@ -248,6 +253,20 @@ class Engine:
         v = C.c_uint64(0)
         self._check(self.lib.ngsq_get_coverage_global(self.h, C.byref(v)))
         return v.value
+
+    # ---- Edits (NGSQ_F_EDITS) ----
+    def set_reference_bases(self, ref: int, letters):
+        """letters: the FASTA sequence of reference `ref` (bytes / uint8 array, line ends removed)."""
+        a = np.frombuffer(letters, dtype=np.uint8) if isinstance(letters, (bytes, bytearray)) else np.ascontiguousarray(letters, dtype=np.uint8)
+        self._check(self.lib.ngsq_set_reference_bases(self.h, ref, a.ctypes.data, a.size))
+
+    def edits(self):
+        """(read_one[513], read_two[513], vaf[101], records stepped through)."""
+        one, two, vaf = np.zeros(513, dtype=np.uint64), np.zeros(513, dtype=np.uint64), np.zeros(101, dtype=np.uint64)
+        n = C.c_uint64(0)
+        u64p = C.POINTER(C.c_uint64)
+        self._check(self.lib.ngsq_get_edits(self.h, one.ctypes.data_as(u64p), two.ctypes.data_as(u64p), vaf.ctypes.data_as(u64p), C.byref(n)))
+        return one, two, vaf, n.value
 
     def stats(self) -> dict:
         st = Stats()

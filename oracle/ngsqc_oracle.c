@@ -680,10 +680,11 @@ typedef struct {
   double mean_read_one, mean_read_two; /* aggregate (edits.rs:336-344) */
   uint64_t records;                    /* records that reached the step-through */
 } edits_t;
-typedef struct { uint64_t* refs; uint64_t* alts; uint64_t start; } edits_pos_ctx;
+typedef struct { uint64_t* refs; uint64_t* alts; uint64_t start, cap; int overflow; } edits_pos_ctx;
 static void edits_on_match(void* c, uint64_t reference_ptr, int is_edit) {
   edits_pos_ctx* x = c;
   uint64_t p = x->start + reference_ptr; /* 1-based reference position (edits.rs:276-278) */
+  if (p > x->cap) { x->overflow = 1; return; } /* increment(position).unwrap() beyond the header's length panics (edits.rs:281-290) */
   if (is_edit) x->alts[p]++; else x->refs[p]++;
 }
 
@@ -736,6 +737,8 @@ void* oracle_edits_run(const uint8_t* bam, size_t bam_len, const uint8_t* bai, s
         if (end == 0) continue;
         if (!(start <= L && end >= 1)) continue;
         if (rec.flag & (0x4 | 0x400)) continue; /* unmapped or duplicate (edits.rs:227-229) */
+        { const char* nm = (const char*)rb.buf + 32; /* read name "*" = missing: the facet bails (edits.rs:233-236) */
+          if (rec.l_name <= 1 || (rec.l_name == 2 && nm[0] == '*')) { snprintf(g_err, sizeof g_err, "Could not parse read name"); return NULL; } }
         /* reference slice start .. start + span, 1-based, end exclusive (edits.rs:241-243,259-262): out of the
          * FASTA sequence -> the reference unwraps a None and panics */
         if (start - 1 + rec.span > seq_len) { snprintf(g_err, sizeof g_err, "record reaches past the end of the reference sequence"); return NULL; }
@@ -747,11 +750,12 @@ void* oracle_edits_run(const uint8_t* bam, size_t bam_len, const uint8_t* bai, s
         }
         uint8_t* qcodes = malloc(rec.l_seq + 1);
         for (uint32_t t = 0; t < rec.l_seq; ++t) qcodes[t] = (t & 1) ? (rec.seq[t >> 1] & 15) : (rec.seq[t >> 1] >> 4);
-        edits_pos_ctx ctx = {refs_pp, alts_pp, start};
+        edits_pos_ctx ctx = {refs_pp, alts_pp, start, L, 0};
         uint64_t edits = 0;
         int st = edits_stepthrough(rcodes, rec.span, qcodes, rec.l_seq, rec.cigar, rec.n_cigar, &edits, edits_on_match, &ctx);
         free(rcodes); free(qcodes);
         if (st) { snprintf(g_err, sizeof g_err, "step-through failed (%d)", st); return NULL; }
+        if (ctx.overflow) { snprintf(g_err, sizeof g_err, "matched position beyond the sequence length of the header"); return NULL; }
         /* increment(edits).unwrap(): more than 512 edits panics the reference (edits.rs:296-300) */
         if (hist_inc_by((rec.flag & 0x40) ? &E->read_one : &E->read_two, edits, 1)) { snprintf(g_err, sizeof g_err, "more than 512 edits in one read"); return NULL; }
         E->records++;

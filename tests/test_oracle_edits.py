@@ -104,8 +104,9 @@ def _python_edits(refseqs, recs):
     return one, two, vaf, n
 
 
-def test_facet_matches_python_restatement():
-    rng = np.random.default_rng(17)
+def make_edits_case(seed=17):
+    """(bam bytes, bai bytes, fasta bytes, reference strings, record dicts): mixed CIGAR shapes, substitutions, flags."""
+    rng = np.random.default_rng(seed)
     refseqs = {name: "".join(rng.choice(list("ACGT"), size=L)) for name, L in REFS}
     recs = []
     for c, (name, L) in enumerate(REFS):
@@ -139,9 +140,27 @@ def test_facet_matches_python_restatement():
                qual=[30] * len(r["seq"])) for r in recs]
     bam, bai = write_bam(REFS, raw, block_payload=3000)
     fasta = "".join(f">{name} synthetic\n" + "\n".join(s[i:i + 60] for i in range(0, len(s), 60)) + "\n" for name, s in refseqs.items())
+    return bam, bai, fasta.encode(), refseqs, recs
+
+
+def oracle_edits(bam: bytes, bai: bytes, fa: bytes):
+    """(read_one, read_two, vaf, records, means) from the oracle, or raises RuntimeError with its message."""
     lib = _lib()
     b, x = as_u8(bam), as_u8(bai)
-    fa = fasta.encode()
+    h = lib.oracle_edits_run(b.ctypes.data, b.size, x.ctypes.data, x.size, fa, len(fa))
+    if not h:
+        raise RuntimeError(lib.oracle_last_error().decode())
+    one, two, vaf = np.zeros(513, np.uint64), np.zeros(513, np.uint64), np.zeros(101, np.uint64)
+    means = (C.c_double * 2)()
+    n = C.c_uint64(0)
+    lib.oracle_edits_get(h, one.ctypes.data, two.ctypes.data, vaf.ctypes.data, means, C.byref(n))
+    return one, two, vaf, n.value, (means[0], means[1])
+
+
+def test_facet_matches_python_restatement():
+    bam, bai, fa, refseqs, recs = make_edits_case(17)
+    lib = _lib()
+    b, x = as_u8(bam), as_u8(bai)
     h = lib.oracle_edits_run(b.ctypes.data, b.size, x.ctypes.data, x.size, fa, len(fa))
     assert h, lib.oracle_last_error().decode()
     one, two, vaf = np.zeros(513, np.uint64), np.zeros(513, np.uint64), np.zeros(101, np.uint64)

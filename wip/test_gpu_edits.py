@@ -1,0 +1,88 @@
+"""GPU parity for the Edits facet: every integer `ngsq_get_edits` returns must equal the oracle's
+on the same BAM + FASTA, and the engine must fail where the oracle (the reference) aborts.  NOT YET RUN ON A GPU: see
+wip/README.md.  Run from the repository root: python -m pytest wip/test_gpu_edits.py -x -q"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from bamutil import as_u8, rec, write_bam  # noqa: E402
+from test_edits_model import ERRORS, _one_record_case  # noqa: E402
+from test_oracle_edits import REFS, make_edits_case, oracle_edits  # noqa: E402
+
+
+def _fasta_sequences(fa: bytes):
+    out, name = {}, None
+    for ln in fa.decode().splitlines():
+        if ln.startswith(">"):
+            name = ln[1:].split()[0]
+            out[name] = []
+        elif name is not None:
+            out[name].append(ln.strip())
+    return {k: "".join(v).encode() for k, v in out.items()}
+
+
+def engine_edits(bam: bytes, fa: bytes, chunk=None):
+    from ngs_b200 import ffi, formats
+    b = as_u8(bam)
+    eng = ffi.Engine(flags=ffi.NGSQ_F_RECORD_FACETS | ffi.NGSQ_F_COVERAGE | ffi.NGSQ_F_VERIFY_CRC | ffi.NGSQ_F_EDITS)
+    hdr = formats.read_header(eng, b)
+    eng.set_references([l for _, l in hdr.refs], [1 if formats.is_primary(n) else 0 for n, _ in hdr.refs])
+    seqs = _fasta_sequences(fa)
+    for c, (name, _) in enumerate(hdr.refs):
+        if name in seqs:
+            eng.set_reference_bases(c, seqs[name])
+    eng.set_range(hdr.first_voffset, 0)
+    eng.submit(np.ascontiguousarray(b), 0)
+    eng.finish()
+    return eng.edits(), eng.stats()
+
+
+@pytest.mark.parametrize("seed", [17, 3, 99])
+def test_edits_match_oracle(seed):
+    bam, bai, fa, _, _ = make_edits_case(seed)
+    one, two, vaf, n, _ = oracle_edits(bam, bai, fa)
+    (g_one, g_two, g_vaf, g_n), st = engine_edits(bam, fa)
+    assert g_n == n > 100
+    np.testing.assert_array_equal(g_one, one)
+    np.testing.assert_array_equal(g_two, two)
+    np.testing.assert_array_equal(g_vaf, vaf)
+    assert st["ms_edits"] > 0
+
+
+@pytest.mark.parametrize("case,code,msg", ERRORS, ids=[str(e[1]) for e in ERRORS])
+def test_engine_fails_where_the_oracle_aborts(case, code, msg):
+    from ngs_b200 import ffi
+    case = dict(case)
+    bam, bai, fa = _one_record_case(case.pop("refseq"), **case)
+    with pytest.raises(RuntimeError, match=msg):
+        oracle_edits(bam, bai, fa)
+    with pytest.raises(ffi.NgsqError) as ei:
+        engine_edits(bam, fa)
+    assert ei.value.code == -11  # NGSQ_E_EDITS
+
+
+def test_other_facets_are_unchanged_by_the_edits_flag():
+    from helpers import assert_same_ints, engine_ints, oracle_ints
+    from ngs_b200 import ffi
+    bam, bai, fa, _, _ = make_edits_case(5)
+    b, x = as_u8(bam), as_u8(bai)
+    want = oracle_ints(b, x, gc_seed=2)
+    got = engine_ints(b, gc_seed=2)
+    assert_same_ints(got, want)
+
+
+def test_a_contig_without_a_sequence_fails_only_if_it_holds_records():
+    from ngs_b200 import ffi
+    ref = "ACGT" * 1250
+    raw = [rec(name="a", flag=0x43, ref=0, pos=100, mapq=9, cigar="20M", seq=ref[100:120])]
+    bam, bai = write_bam(REFS, raw)
+    (one, two, vaf, n), _ = engine_edits(bam, f">chr1\n{ref}\n".encode())   # chr2 / chrM have no sequence and no records
+    assert n == 1 and one[0] == 1 and int(vaf.sum()) == 20
+    with pytest.raises(ffi.NgsqError):
+        engine_edits(bam, b">chr2\nACGT\n")
