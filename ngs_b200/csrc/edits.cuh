@@ -126,6 +126,8 @@ NGSQ_HD uint32_t edits_record(const uint8_t* rec, int32_t n_ref, const EditsCont
   const uint32_t w3 = ed_ld32(rec + 12), w4 = ed_ld32(rec + 16), lseq = ed_ld32(rec + 20);
   const uint32_t lname = w3 & 255, ncig = w4 & 0xFFFF, flag = w4 >> 16;
   if (ref < 0 || ref >= n_ref || pos < 0) return kEdSkipped;  // not returned by the per-contig query (command.rs:369-377)
+  // a record whose fields overrun its block_size fails the run in the facet kernel (R_ERR_RECORD): never walk it
+  if (32ull + lname + 4ull * ncig + (lseq + 1ull) / 2 + lseq > ed_ld32(rec)) return kEdSkipped;
   const uint8_t* cig = rec + 36 + lname;
   const uint8_t* seq = cig + 4 * (size_t)ncig;
   uint64_t span = 0;
