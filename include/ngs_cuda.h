@@ -52,7 +52,8 @@ enum {
   NGSQ_E_CHAIN = -8,      /* record-boundary closure check failed */
   NGSQ_E_NCCL = -9,
   NGSQ_E_NOMEM = -10,
-  NGSQ_E_EDITS = -11      /* the Edits facet met a record / reference the reference program aborts on */
+  NGSQ_E_EDITS = -11,     /* the Edits facet met a record / reference the reference program aborts on */
+  NGSQ_E_FEATURES = -12   /* likewise for the Genomic Features facet */
 };
 
 /* ngsq_config.flags */
@@ -61,6 +62,7 @@ enum {
 #define NGSQ_F_VERIFY_CRC 4u    /* verify the CRC32 of every block (reference behaviour) */
 #define NGSQ_F_EDITS 8u         /* Edits (needs ngsq_set_reference_bases for every contig that holds records);
                                    written against the oracle and a host model, not yet measured on a GPU */
+#define NGSQ_F_FEATURES 16u     /* Genomic Features (needs ngsq_set_feature_model + ngsq_set_features); same status */
 
 typedef struct ngsq_engine ngsq_engine;
 
@@ -124,6 +126,17 @@ int ngsq_set_references(ngsq_engine* e, uint32_t n_ref, const uint32_t* ref_len,
  * for contigs the FASTA lacks (a record on a contig without a sequence fails the run).  Needs NGSQ_F_EDITS. */
 int ngsq_set_reference_bases(ngsq_engine* e, uint32_t ref, const uint8_t* letters, uint64_t n);
 
+/* Genomic Features facet (src/qc/record_based/features.rs:270-355, try_from): the gene model, filed the way the
+ * reference files it.  The five configured feature names are slots 0 five_prime_utr, 1 three_prime_utr,
+ * 2 coding_sequence, 3 exon, 4 gene (command.rs:78-101); names may coincide, so slot_class[j] = the smallest slot index
+ * whose name equals slot j's.  primary[c] = reference c is in the genome's primary assembly (features.rs:157-164).
+ * Then, per primary reference, every GFF record whose type equals one of the names: start, end (1-based, as they stand
+ * in the GFF; end is used as an exclusive bound like the reference does) and cls = slot_class of the FIRST slot whose
+ * name equals the type.  GFF parsing, the strand check of features/utils.rs:33-43 and "unwrap every record" stay on the
+ * caller's side.  After ngsq_set_references, before the first submit.  Needs NGSQ_F_FEATURES. */
+int ngsq_set_feature_model(ngsq_engine* e, const uint8_t slot_class[5], const uint8_t* primary);
+int ngsq_set_features(ngsq_engine* e, uint32_t ref, uint32_t n, const uint32_t* start, const uint32_t* stop, const uint8_t* cls);
+
 /* Virtual offsets (coffset << 16 | uoffset) of the first record this shard owns and of the
  * first record it does NOT own (0 = everything to the end of the submitted data).  Both must
  * be true record starts (after the header for shard 0; BAI anchors otherwise). */
@@ -176,6 +189,9 @@ int ngsq_get_coverage_global(ngsq_engine* e, uint64_t* nonsensical_records);
 /* Edits (edits.rs:22-46): the integer state of EditMetrics when aggregate() runs — read_one_edits / read_two_edits
  * (Histogram 0..=512 of edits per read), vaf_histogram (0..=100, filled by teardown, edits.rs:318-334) and the number
  * of records that were stepped through.  The two means of the summary are the caller's (Histogram::mean). */
+/* Genomic Features (features/metrics.rs): utr_five_prime_count, utr_three_prime_count, coding_sequence_count,
+ * intergenic_count, exonic_count, intronic_count, processed, ignored_flags, ignored_nonprimary_chromosome. */
+int ngsq_get_features(ngsq_engine* e, uint64_t counts[9]);
 int ngsq_get_edits(ngsq_engine* e, uint64_t read_one[513], uint64_t read_two[513], uint64_t vaf[101], uint64_t* records);
 int ngsq_get_stats(ngsq_engine* e, ngsq_stats* out);
 

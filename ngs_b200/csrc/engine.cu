@@ -22,6 +22,7 @@
 #include "crc32.cuh"
 #include "edits.cuh"
 #include "facets.cuh"
+#include "features.cuh"
 #include "inflate2.cuh"
 #include "recscan.cuh"
 
@@ -154,6 +155,15 @@ struct ngsq_engine {
   std::vector<uint64_t> h_ed_res;
   cudaEvent_t ev_g = nullptr;
 
+  // Genomic Features facet (NGSQ_F_FEATURES): per contig and class, sorted starts / stops; nine counters
+  std::vector<FeatureContig> ft_contigs;
+  std::vector<void*> ft_allocs;
+  FeatureContig* d_ft_contigs = nullptr;
+  uint8_t ft_slot_class[8] = {0, 1, 2, 3, 4, 0, 0, 0};
+  bool ft_model_set = false;
+  unsigned long long* d_ft_res = nullptr;
+  std::vector<uint64_t> h_ft_res;
+
   // nccl
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -225,6 +235,7 @@ int start_run(ngsq_engine* e) {
   if ((e->cfg.flags & NGSQ_F_COVERAGE) && e->diff_elems) CU(cudaMemsetAsync(e->d_diff, 0, e->diff_elems * 4, e->s_comp));
   CU(cudaMemsetAsync(e->d_queue, 0, ngsq_engine::kQueueSlots * 4, e->s_comp));
   CU(cudaMemsetAsync(e->d_flags, 0, sizeof(DevFlags), e->s_comp));
+  if ((e->cfg.flags & NGSQ_F_FEATURES) && e->d_ft_res) CU(cudaMemsetAsync(e->d_ft_res, 0, F_WORDS * 8, e->s_comp));
   if ((e->cfg.flags & NGSQ_F_EDITS) && e->d_ed_res) {
     CU(cudaMemsetAsync(e->d_ed_res, 0, E_WORDS * 8, e->s_comp));
     if (e->ed_pos_total) {
@@ -491,6 +502,8 @@ void ngsq_destroy(ngsq_engine* e) {
   for (void* p : ptrs) if (p) cudaFree(p);
   for (void* p : e->ed_allocs) cudaFree(p);
   for (void* p : {(void*)e->d_ed_contigs, (void*)e->d_ed_refs, (void*)e->d_ed_alts, (void*)e->d_ed_res}) if (p) cudaFree(p);
+  for (void* p : e->ft_allocs) cudaFree(p);
+  for (void* p : {(void*)e->d_ft_contigs, (void*)e->d_ft_res}) if (p) cudaFree(p);
   for (auto& sg : e->comp_segs) cudaFree(sg.ptr);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
@@ -525,6 +538,7 @@ int ngsq_reset(ngsq_engine* e) {
   e->run_started = false; e->finished = false;
   e->h_res.clear(); e->h_qpos = 0;
   e->h_ed_res.clear();
+  e->h_ft_res.clear();
   memset(&e->stats, 0, sizeof e->stats);
   return NGSQ_OK;
 }
@@ -593,6 +607,65 @@ int ngsq_set_references(ngsq_engine* e, uint32_t n_ref, const uint32_t* ref_len,
     }
     if (!e->d_ed_res) CU(cudaMalloc(&e->d_ed_res, E_WORDS * 8));
   }
+  if (e->cfg.flags & NGSQ_F_FEATURES) {
+    for (void* p : e->ft_allocs) cudaFree(p);
+    e->ft_allocs.clear();
+    if (e->d_ft_contigs) cudaFree(e->d_ft_contigs);
+    e->d_ft_contigs = nullptr;
+    e->ft_contigs.assign(n_ref, FeatureContig{});
+    e->ft_model_set = false;
+    CU(cudaMalloc(&e->d_ft_contigs, nr * sizeof(FeatureContig)));
+    if (n_ref) CU(cudaMemcpy(e->d_ft_contigs, e->ft_contigs.data(), n_ref * sizeof(FeatureContig), cudaMemcpyHostToDevice));
+    if (!e->d_ft_res) CU(cudaMalloc(&e->d_ft_res, F_WORDS * 8));
+  }
+  return NGSQ_OK;
+}
+
+int ngsq_set_feature_model(ngsq_engine* e, const uint8_t slot_class[5], const uint8_t* primary) {
+  if (!e || !slot_class || (e->n_ref && !primary)) return fail(e, NGSQ_E_ARG, "bad feature model");
+  if (!(e->cfg.flags & NGSQ_F_FEATURES)) return fail(e, NGSQ_E_ARG, "the engine was created without NGSQ_F_FEATURES");
+  if (e->ft_contigs.size() != e->n_ref) return fail(e, NGSQ_E_ARG, "ngsq_set_feature_model must follow ngsq_set_references");
+  if (e->run_started) return fail(e, NGSQ_E_ARG, "ngsq_set_feature_model must precede the first submit");
+  for (int j = 0; j < 5; ++j)
+    if (slot_class[j] > j || slot_class[slot_class[j]] != slot_class[j]) return fail(e, NGSQ_E_ARG, "slot_class[%d] must name the first slot with the same feature name", j);
+  CU(cudaSetDevice(e->device));
+  memcpy(e->ft_slot_class, slot_class, 5);
+  for (uint32_t c = 0; c < e->n_ref; ++c) e->ft_contigs[c].primary = primary[c] ? 1u : 0u;
+  if (e->n_ref) CU(cudaMemcpy(e->d_ft_contigs, e->ft_contigs.data(), e->n_ref * sizeof(FeatureContig), cudaMemcpyHostToDevice));
+  e->ft_model_set = true;
+  return NGSQ_OK;
+}
+
+int ngsq_set_features(ngsq_engine* e, uint32_t ref, uint32_t n, const uint32_t* start, const uint32_t* stop, const uint8_t* cls) {
+  if (!e || (n && (!start || !stop || !cls))) return fail(e, NGSQ_E_ARG, "bad features");
+  if (!(e->cfg.flags & NGSQ_F_FEATURES)) return fail(e, NGSQ_E_ARG, "the engine was created without NGSQ_F_FEATURES");
+  if (ref >= e->n_ref || e->ft_contigs.size() != e->n_ref) return fail(e, NGSQ_E_ARG, "ngsq_set_features: reference %u is not in the header given to ngsq_set_references", ref);
+  if (e->run_started) return fail(e, NGSQ_E_ARG, "ngsq_set_features must precede the first submit");
+  CU(cudaSetDevice(e->device));
+  FeatureContig& C = e->ft_contigs[ref];
+  for (int k = 0; k < 5; ++k) if (C.n[k]) return fail(e, NGSQ_E_ARG, "reference %u already has features", ref);
+  std::vector<uint32_t> a[5], b[5];
+  for (uint32_t i = 0; i < n; ++i) {
+    if (cls[i] > 4) return fail(e, NGSQ_E_ARG, "feature class %u out of range", cls[i]);
+    if (start[i] > stop[i]) return fail(e, NGSQ_E_ARG, "feature %u has start > end (%u > %u): not supported by the counting lookup", i, start[i], stop[i]);
+    a[cls[i]].push_back(start[i]);
+    b[cls[i]].push_back(stop[i]);
+  }
+  for (int k = 0; k < 5; ++k) {
+    if (a[k].empty()) continue;
+    std::sort(a[k].begin(), a[k].end());
+    std::sort(b[k].begin(), b[k].end());
+    uint32_t *da = nullptr, *db = nullptr;
+    const size_t bytes = a[k].size() * 4;
+    cudaError_t rc = cudaMalloc(&da, bytes);
+    if (rc == cudaSuccess) { e->ft_allocs.push_back(da); rc = cudaMalloc(&db, bytes); }
+    if (rc != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc features (%zu bytes): %s", bytes, cudaGetErrorString(rc));
+    e->ft_allocs.push_back(db);
+    CU(cudaMemcpy(da, a[k].data(), bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db, b[k].data(), bytes, cudaMemcpyHostToDevice));
+    C.starts[k] = da; C.stops[k] = db; C.n[k] = (uint32_t)a[k].size();
+  }
+  CU(cudaMemcpy(e->d_ft_contigs + ref, &C, sizeof C, cudaMemcpyHostToDevice));
   return NGSQ_OK;
 }
 
@@ -910,6 +983,23 @@ int ngsq_finish(ngsq_engine* e) {
     e->h_ed_res.resize(E_WORDS);
     CU(cudaMemcpyAsync(e->h_ed_res.data(), e->d_ed_res, E_WORDS * 8, cudaMemcpyDeviceToHost, s));
   }
+  // K11 (NGSQ_F_FEATURES): per-record overlap counts against the gene model
+  const bool do_features = (e->cfg.flags & NGSQ_F_FEATURES) && e->d_ft_res && e->ft_model_set && e->ft_contigs.size() == e->n_ref;
+  if ((e->cfg.flags & NGSQ_F_FEATURES) && !do_features) return fail(e, NGSQ_E_ARG, "NGSQ_F_FEATURES needs ngsq_set_feature_model before the first submit");
+  if (do_features && n_rec) {
+    FeatureParams FP{};
+    FP.d = e->d_out; FP.rec = e->d_rec; FP.n_rec = n_rec; FP.max_records = e->cfg.max_records; FP.out_off = e->d_out_off; FP.n_ref = (int32_t)e->n_ref;
+    FP.contigs = e->d_ft_contigs; FP.res = e->d_ft_res;
+    memcpy(FP.slot_class, e->ft_slot_class, 8);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((n_rec + 255) / 256, (uint64_t)e->n_sm * 8);
+    features_kernel<<<grid, 256, 0, s>>>(FP);
+    CU(cudaGetLastError());
+    e->other_launches += 1;
+  }
+  if (do_features) {
+    e->h_ft_res.resize(F_WORDS);
+    CU(cudaMemcpyAsync(e->h_ft_res.data(), e->d_ft_res, F_WORDS * 8, cudaMemcpyDeviceToHost, s));
+  }
   CU(cudaEventRecord(e->ev_g, s));
   // the step ends when the CRC stream is done too (its last event closes the device-timed region)
   if (!e->inflate_events.empty()) CU(cudaStreamWaitEvent(s, e->inflate_events.back().crc_end, 0));
@@ -954,6 +1044,20 @@ int ngsq_finish(ngsq_engine* e) {
     const uint64_t k = e->h_ed_res[E_ERR];
     return fail(e, NGSQ_E_EDITS, "Edits: %s (the reference aborts the run here)", k < sizeof kinds / sizeof *kinds ? kinds[k] : "unknown failure");
   }
+  if (do_features && e->h_ft_res[F_ERR]) {
+    static const char* const kinds[] = {"", "Could not parse read name", "Could not parse reference sequence id for read", "Could not parse record's start position.",
+                                        "invalid CIGAR operation"};
+    const uint64_t k = e->h_ft_res[F_ERR];
+    return fail(e, NGSQ_E_FEATURES, "Genomic Features: %s (the reference aborts the run here)", k < sizeof kinds / sizeof *kinds ? kinds[k] : "unknown failure");
+  }
+  return NGSQ_OK;
+}
+
+int ngsq_get_features(ngsq_engine* e, uint64_t counts[9]) {
+  if (!e || !counts) return NGSQ_E_ARG;
+  if (!e->finished || e->h_ft_res.size() != F_WORDS) return fail(e, NGSQ_E_ARG, "Genomic Features results requested before ngsq_finish or without NGSQ_F_FEATURES");
+  if (e->h_ft_res[F_ERR]) return fail(e, NGSQ_E_FEATURES, "the Genomic Features facet failed; no results");
+  memcpy(counts, e->h_ft_res.data(), 9 * 8);
   return NGSQ_OK;
 }
 
@@ -1122,6 +1226,13 @@ int ngsq_reduce(ngsq_engine* e, int root) {
     rc = g_nccl.Reduce(e->d_ed_res, e->d_ed_res, E_WORDS, ncclUint64, ncclSum, root, e->comm, s);
     if (rc) return fail(e, NGSQ_E_NCCL, "ncclReduce (edits): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     CU(cudaMemcpyAsync(e->h_ed_res.data(), e->d_ed_res, E_WORDS * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    e->other_launches += 1;
+  }
+  if ((e->cfg.flags & NGSQ_F_FEATURES) && e->d_ft_res && e->h_ft_res.size() == F_WORDS) {
+    rc = g_nccl.Reduce(e->d_ft_res, e->d_ft_res, F_WORDS, ncclUint64, ncclSum, root, e->comm, s);
+    if (rc) return fail(e, NGSQ_E_NCCL, "ncclReduce (features): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    CU(cudaMemcpyAsync(e->h_ft_res.data(), e->d_ft_res, F_WORDS * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     e->other_launches += 1;
   }

@@ -20,11 +20,12 @@ NGSQ_F_RECORD_FACETS = 1
 NGSQ_F_COVERAGE = 2
 NGSQ_F_VERIFY_CRC = 4
 NGSQ_F_EDITS = 8
+NGSQ_F_FEATURES = 16
 
 ERROR_NAMES = {
     0: "NGSQ_OK", -1: "NGSQ_E_ARG", -2: "NGSQ_E_CUDA", -3: "NGSQ_E_TRUNCATED", -4: "NGSQ_E_BAD_BLOCK",
     -5: "NGSQ_E_CRC", -6: "NGSQ_E_BAD_RECORD", -7: "NGSQ_E_QUAL_RANGE", -8: "NGSQ_E_CHAIN",
-    -9: "NGSQ_E_NCCL", -10: "NGSQ_E_NOMEM", -11: "NGSQ_E_EDITS",
+    -9: "NGSQ_E_NCCL", -10: "NGSQ_E_NOMEM", -11: "NGSQ_E_EDITS", -12: "NGSQ_E_FEATURES",
 }
 
 # every symbol include/ngs_cuda.h declares (tests check the library exports all of them)
@@ -34,7 +35,7 @@ EXPORTED = [
     "ngsq_get_tlen", "ngsq_get_gc", "ngsq_get_quality", "ngsq_get_coverage_contig", "ngsq_get_coverage_global",
     "ngsq_get_stats", "ngsq_nccl_unique_id", "ngsq_comm_init", "ngsq_reduce", "ngsq_set_quality_positions",
     "ngsq_result_buffer", "ngsq_refresh_results", "ngsq_host_alloc", "ngsq_host_free", "ngsq_inflate_to_host",
-    "ngsq_set_reference_bases", "ngsq_get_edits",
+    "ngsq_set_reference_bases", "ngsq_get_edits", "ngsq_set_feature_model", "ngsq_set_features", "ngsq_get_features",
 ]
 
 
@@ -120,6 +121,9 @@ def load_library() -> C.CDLL:
     lib.ngsq_inflate_to_host.argtypes = [P, P, C.c_size_t, P, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.ngsq_set_reference_bases.argtypes = [P, C.c_uint32, P, C.c_uint64]
     lib.ngsq_get_edits.argtypes = [P, u64p, u64p, u64p, u64p]
+    lib.ngsq_set_feature_model.argtypes = [P, u8p, u8p]
+    lib.ngsq_set_features.argtypes = [P, C.c_uint32, C.c_uint32, u32p, u32p, u8p]
+    lib.ngsq_get_features.argtypes = [P, u64p]
     _lib = lib
     return lib
 
@@ -267,6 +271,26 @@ class Engine:
         u64p = C.POINTER(C.c_uint64)
         self._check(self.lib.ngsq_get_edits(self.h, one.ctypes.data_as(u64p), two.ctypes.data_as(u64p), vaf.ctypes.data_as(u64p), C.byref(n)))
         return one, two, vaf, n.value
+
+    # ---- Genomic Features (NGSQ_F_FEATURES) ----
+    def set_feature_model(self, names, primary):
+        """names: the five configured feature names (5' UTR, 3' UTR, CDS, exon, gene); returns slot_class."""
+        sc = np.array([min(i for i in range(5) if names[i] == names[j]) for j in range(5)], dtype=np.uint8)
+        pr = np.ascontiguousarray(primary, dtype=np.uint8)
+        u8p = C.POINTER(C.c_uint8)
+        self._check(self.lib.ngsq_set_feature_model(self.h, sc.ctypes.data_as(u8p), pr.ctypes.data_as(u8p)))
+        return sc
+
+    def set_features(self, ref: int, start, stop, cls):
+        a, b = np.ascontiguousarray(start, dtype=np.uint32), np.ascontiguousarray(stop, dtype=np.uint32)
+        k = np.ascontiguousarray(cls, dtype=np.uint8)
+        u32p = C.POINTER(C.c_uint32)
+        self._check(self.lib.ngsq_set_features(self.h, ref, a.size, a.ctypes.data_as(u32p), b.ctypes.data_as(u32p), k.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def features(self) -> np.ndarray:
+        out = np.zeros(9, dtype=np.uint64)
+        self._check(self.lib.ngsq_get_features(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
 
     def stats(self) -> dict:
         st = Stats()
