@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/ngs_cuda.h"
+#include "gene_model.hpp"
 #include "genome.hpp"
 #include "results.hpp"
 
@@ -224,6 +225,93 @@ class CoverageFacet : public SequenceBasedQualityControlFacet {
   CoverageMetrics metrics_;
   std::vector<Sequence> primary_assembly_;
   uint64_t bin_size_;
+};
+
+// ---- Genomic Features (src/qc/record_based/features.rs) — device path written, not yet verified on a GPU ----
+class GenomicFeaturesFacet : public RecordBasedQualityControlFacet {
+ public:
+  FeaturesMetrics metrics;
+  // features.rs:270-355: reads and files the gene model; throws where the reference errors or panics
+  static GenomicFeaturesFacet try_from(const std::string& src, const FeatureNames& names, const ReferenceGenome& genome) {
+    GenomicFeaturesFacet f;
+    f.names_ = names;
+    f.model_ = read_gene_model(slurp_maybe_gz(src, "GFF"), names, genome);
+    for (auto& s : get_primary_assembly(genome)) f.primary_.push_back(s.name);
+    return f;
+  }
+  const char* name() const override { return "Genomic Features"; }
+  ComputationalLoad computational_load() const override { return ComputationalLoad::Moderate; }
+  // hands the model to an engine (after ngsq_set_references, before the first submit)
+  void upload(ngsq_engine* e, const std::vector<ReferenceSequence>& header) const {
+    std::vector<uint8_t> primary(header.size(), 0);
+    for (size_t c = 0; c < header.size(); ++c)
+      for (auto& p : primary_) if (p == header[c].name) primary[c] = 1;
+    const auto sc = names_.slot_class();
+    check(e, ngsq_set_feature_model(e, sc.data(), primary.data()));
+    for (size_t c = 0; c < header.size(); ++c) {
+      auto it = model_.find(header[c].name);
+      if (it == model_.end() || !primary[c]) continue;
+      const ContigFeatures& m = it->second;
+      check(e, ngsq_set_features(e, (uint32_t)c, (uint32_t)m.start.size(), m.start.data(), m.stop.data(), m.cls.data()));
+    }
+  }
+  void ingest(ngsq_engine* e) override {
+    uint64_t c[9];
+    check(e, ngsq_get_features(e, c));
+    metrics.utr_five_prime_count = c[0]; metrics.utr_three_prime_count = c[1]; metrics.coding_sequence_count = c[2];
+    metrics.intergenic_count = c[3]; metrics.exonic_count = c[4]; metrics.intronic_count = c[5];
+    metrics.processed = c[6]; metrics.ignored_flags = c[7]; metrics.ignored_nonprimary_chromosome = c[8];
+  }
+  void summarize() override {  // features.rs:244-262 (integer sum first, then `as f64`)
+    const double total = (double)(metrics.ignored_flags + metrics.ignored_nonprimary_chromosome + metrics.processed);
+    metrics.summary = std::make_pair(((double)metrics.ignored_flags / total) * 100.0, ((double)metrics.ignored_nonprimary_chromosome / total) * 100.0);
+  }
+  void aggregate(Results& results) const override { results.features = metrics; }
+  const std::map<std::string, ContigFeatures>& model() const { return model_; }
+
+ private:
+  FeatureNames names_;
+  std::map<std::string, ContigFeatures> model_;
+  std::vector<std::string> primary_;
+};
+
+// ---- Edits (src/qc/sequence_based/edits.rs) — device path written, not yet verified on a GPU ----
+class EditsFacet : public SequenceBasedQualityControlFacet {
+ public:
+  EditMetrics metrics;
+  // edits.rs:64-105 (the VAF file option is not offered: per-position VAFs stay on the device)
+  static EditsFacet try_from(const std::string& reference_fasta) {
+    EditsFacet f;
+    f.sequences_ = read_fasta(slurp_maybe_gz(reference_fasta, "reference FASTA"));
+    return f;
+  }
+  const char* name() const override { return "Edits"; }
+  ComputationalLoad computational_load() const override { return ComputationalLoad::Heavy; }
+  bool supports_sequence_name(const std::string&) const override { return true; }  // edits.rs:178-180
+  void upload(ngsq_engine* e, const std::vector<ReferenceSequence>& header) const {
+    for (size_t c = 0; c < header.size(); ++c) {
+      auto it = sequences_.find(header[c].name);
+      if (it == sequences_.end()) throw std::runtime_error("sequence " + header[c].name + " not found in reference FASTA.");  // edits.rs:205-207
+      check(e, ngsq_set_reference_bases(e, (uint32_t)c, reinterpret_cast<const uint8_t*>(it->second.data()), it->second.size()));
+    }
+  }
+  void ingest_global(ngsq_engine* e) override {
+    std::vector<uint64_t> one(513), two(513), vaf(101);
+    uint64_t records = 0;
+    check(e, ngsq_get_edits(e, one.data(), two.data(), vaf.data(), &records));
+    metrics.read_one_edits.fill_from(one.data(), 513);
+    metrics.read_two_edits.fill_from(two.data(), 513);
+    metrics.vaf_histogram.fill_from(vaf.data(), 101);
+  }
+  void ingest(ngsq_engine*, uint32_t, const ReferenceSequence&) override {}
+  void teardown(const ReferenceSequence&) override {}  // edits.rs:305-334 ran on the device (edits_vaf_kernel)
+  void aggregate(Results& results) override {          // edits.rs:336-344
+    metrics.summary = std::make_pair(metrics.read_one_edits.mean(), metrics.read_two_edits.mean());
+    results.edits = metrics;
+  }
+
+ private:
+  std::map<std::string, std::string> sequences_;
 };
 
 // src/qc.rs:44-126 — default facet set and the `--only` filter.  Genomic Features (needs a GFF)

@@ -58,15 +58,30 @@ struct CoverageMetrics {
   std::vector<std::string> covered_by_order;  // "10x".."60x" in insertion order
 };
 
+// features/metrics.rs:8-80
+struct FeaturesMetrics {
+  uint64_t utr_five_prime_count = 0, utr_three_prime_count = 0, coding_sequence_count = 0;   // exonic_translation_regions
+  uint64_t intergenic_count = 0, exonic_count = 0, intronic_count = 0;                       // gene_regions
+  uint64_t processed = 0, ignored_flags = 0, ignored_nonprimary_chromosome = 0;              // records
+  std::optional<std::pair<double, double>> summary;  // ignored_flags_pct, ignored_nonprimary_chromosome_pct
+};
+
+// edits.rs:22-62
+struct EditMetrics {
+  Histogram read_one_edits, read_two_edits;                                  // Histogram::default() = 0..=512
+  Histogram vaf_histogram = Histogram::zero_based_with_capacity(100);
+  std::optional<std::pair<double, double>> summary;  // mean_edits_read_one, mean_edits_read_two
+};
+
 // results.rs:24-45
 struct Results {
   std::optional<GeneralMetrics> general;
-  // features: Genomic Features facet is out of scope for the CUDA engine (always null)
+  std::optional<FeaturesMetrics> features;  // filled only by the Genomic Features facet (device path not yet verified on a GPU)
   std::optional<GCContentMetrics> gc_content;
   std::optional<TemplateLengthMetrics> template_length;
   std::optional<QualityScoreMetrics> quality_scores;
   std::optional<CoverageMetrics> coverage;
-  // edits: Edits facet is out of scope (always null)
+  std::optional<EditMetrics> edits;         // filled only by the Edits facet (device path not yet verified on a GPU)
 
   static void write_hist(JsonWriter& w, const Histogram& h) {  // histogram.rs:152-159 field order
     w.begin_object();
@@ -111,7 +126,30 @@ struct Results {
       }
       w.end_object();
     }
-    w.key("features"); w.value_null();
+    w.key("features");
+    if (!features) w.value_null();
+    else {
+      const auto& f = *features;
+      w.begin_object();
+      w.key("exonic_translation_regions"); w.begin_object();
+      w.key("utr_five_prime_count"); w.value_u64(f.utr_five_prime_count); w.key("utr_three_prime_count"); w.value_u64(f.utr_three_prime_count);
+      w.key("coding_sequence_count"); w.value_u64(f.coding_sequence_count); w.end_object();
+      w.key("gene_regions"); w.begin_object();
+      w.key("intergenic_count"); w.value_u64(f.intergenic_count); w.key("exonic_count"); w.value_u64(f.exonic_count);
+      w.key("intronic_count"); w.value_u64(f.intronic_count); w.end_object();
+      w.key("records"); w.begin_object();
+      w.key("processed"); w.value_u64(f.processed); w.key("ignored_flags"); w.value_u64(f.ignored_flags);
+      w.key("ignored_nonprimary_chromosome"); w.value_u64(f.ignored_nonprimary_chromosome); w.end_object();
+      w.key("summary");
+      if (!f.summary) w.value_null();
+      else {
+        w.begin_object();
+        w.key("ignored_flags_pct"); w.value_f64(f.summary->first);
+        w.key("ignored_nonprimary_chromosome_pct"); w.value_f64(f.summary->second);
+        w.end_object();
+      }
+      w.end_object();
+    }
     w.key("gc_content");
     if (!gc_content) w.value_null();
     else {
@@ -182,7 +220,23 @@ struct Results {
       w.key("genome_covered_by"); w.begin_object(); for (auto& k : c.covered_by_order) { w.key(k); w.value_f32(c.genome_covered_by.at(k)); } w.end_object();
       w.end_object();
     }
-    w.key("edits"); w.value_null();
+    w.key("edits");
+    if (!edits) w.value_null();
+    else {
+      w.begin_object();
+      w.key("read_one_edits"); write_hist(w, edits->read_one_edits);
+      w.key("read_two_edits"); write_hist(w, edits->read_two_edits);
+      w.key("vaf_histogram"); write_hist(w, edits->vaf_histogram);
+      w.key("summary");
+      if (!edits->summary) w.value_null();
+      else {
+        w.begin_object();
+        w.key("mean_edits_read_one"); w.value_f64(edits->summary->first);
+        w.key("mean_edits_read_two"); w.value_f64(edits->summary->second);
+        w.end_object();
+      }
+      w.end_object();
+    }
     w.end_object();
     return w.out;
   }

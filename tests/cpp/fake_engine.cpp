@@ -77,3 +77,28 @@ int ngsq_get_coverage_contig(ngsq_engine*, uint32_t ref, ngsq_cov_ints* out, uin
 }
 int ngsq_get_coverage_global(ngsq_engine*, uint64_t* nonsensical_records) { load(); *nonsensical_records = g.nonsensical; return 0; }
 }
+
+// ---- the two "next" facets: integers from $NGSQ_FAKE_NEXT = 9 feature counters, read_one[513], read_two[513], vaf[101], records
+namespace {
+std::vector<uint64_t> g_next;
+void load_next() {
+  if (!g_next.empty()) return;
+  const char* p = getenv("NGSQ_FAKE_NEXT");
+  FILE* f = p ? fopen(p, "rb") : nullptr;
+  if (!f) { fprintf(stderr, "fake engine: NGSQ_FAKE_NEXT not readable\n"); exit(2); }
+  g_next = rd(f, 9 + 513 + 513 + 101 + 1);
+  fclose(f);
+}
+}  // namespace
+extern "C" {
+int ngsq_get_features(ngsq_engine*, uint64_t counts[9]) { load_next(); memcpy(counts, g_next.data(), 72); return 0; }
+int ngsq_get_edits(ngsq_engine*, uint64_t read_one[513], uint64_t read_two[513], uint64_t vaf[101], uint64_t* records) {
+  load_next();
+  memcpy(read_one, &g_next[9], 513 * 8); memcpy(read_two, &g_next[9 + 513], 513 * 8); memcpy(vaf, &g_next[9 + 1026], 101 * 8);
+  if (records) *records = g_next[9 + 1127];
+  return 0;
+}
+int ngsq_set_feature_model(ngsq_engine*, const uint8_t*, const uint8_t*) { return 0; }
+int ngsq_set_features(ngsq_engine*, uint32_t, uint32_t, const uint32_t*, const uint32_t*, const uint8_t*) { return 0; }
+int ngsq_set_reference_bases(ngsq_engine*, uint32_t, const uint8_t*, uint64_t) { return 0; }
+}
