@@ -1,4 +1,4 @@
-// K10 — the Edits facet (reference: src/qc/sequence_based/edits.rs:217-344 over
+// K11 — the Edits facet (reference: src/qc/sequence_based/edits.rs:217-344 over
 // src/utils/alignment.rs:48-107 and src/utils/cigar.rs:6-23): per record, the number of M-positions whose read
 // base differs from the reference FASTA base, per reference position the counts of matching / differing reads,
 // and at the end of the run the histogram of per-position variant allele fractions.

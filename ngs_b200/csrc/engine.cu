@@ -964,7 +964,7 @@ int ngsq_finish(ngsq_engine* e) {
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(e->ev_e, s));
-  // K10 (NGSQ_F_EDITS): per-record edit counts and per-position ref / alt counters, then the VAF histogram
+  // K11 (NGSQ_F_EDITS): per-record edit counts and per-position ref / alt counters, then the VAF histogram
   const bool do_edits = (e->cfg.flags & NGSQ_F_EDITS) && e->d_ed_res && e->ed_contigs.size() == e->n_ref;
   if (do_edits && n_rec) {
     EditsParams EP{};
@@ -983,7 +983,7 @@ int ngsq_finish(ngsq_engine* e) {
     e->h_ed_res.resize(E_WORDS);
     CU(cudaMemcpyAsync(e->h_ed_res.data(), e->d_ed_res, E_WORDS * 8, cudaMemcpyDeviceToHost, s));
   }
-  // K11 (NGSQ_F_FEATURES): per-record overlap counts against the gene model
+  // K12 (NGSQ_F_FEATURES): per-record overlap counts against the gene model
   const bool do_features = (e->cfg.flags & NGSQ_F_FEATURES) && e->d_ft_res && e->ft_model_set && e->ft_contigs.size() == e->n_ref;
   if ((e->cfg.flags & NGSQ_F_FEATURES) && !do_features) return fail(e, NGSQ_E_ARG, "NGSQ_F_FEATURES needs ngsq_set_feature_model before the first submit");
   if (do_features && n_rec) {

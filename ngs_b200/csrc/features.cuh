@@ -1,4 +1,4 @@
-// K11 — the Genomic Features facet (reference: src/qc/record_based/features.rs:115-242 over the
+// K12 — the Genomic Features facet (reference: src/qc/record_based/features.rs:115-242 over the
 // rust-lapper interval lookups built by try_from, 270-355): per record, which kinds of gene-model features its
 // alignment interval overlaps — 5' UTR / 3' UTR / CDS tallies and exonic / intronic / intergenic.
 //
