@@ -19,9 +19,9 @@ REFS = [("chr1", 100000), ("chr2", 50000)]
 
 def _case():
     fake = b"".join(record(name="d", flag=0, ref=0, pos=5 + i, mapq=30, cigar="10M", seq="ACGTACGTAC", qual=[30] * 10) for i in range(3))
-    before = [rec(name=f"a{i}", flag=0x43, ref=0, pos=100 + 7 * i, mapq=30, cigar="50M", seq="ACGTA" * 10, qual=[25] * 50) for i in range(40)]
-    host = rec(name="host", flag=0x83, ref=0, pos=500, mapq=30, cigar="50M", seq="TTGCA" * 10, qual=[35] * 50, aux=fake + b"\x00" * 7)
-    after = [rec(name=f"b{i}", flag=0x43, ref=1, pos=10 + 9 * i, mapq=30, cigar="20M5D30M", seq="GGCAT" * 10, qual=[20] * 50) for i in range(60)]
+    before = [rec(name=f"a{i}", flag=0x43, ref=0, pos=100 + 7 * i, next_ref=0, next_pos=300, tlen=250, mapq=30, cigar="50M", seq="ACGTA" * 10, qual=[25] * 50) for i in range(40)]
+    host = rec(name="host", flag=0x83, ref=0, pos=500, next_ref=0, next_pos=100, tlen=-450, mapq=30, cigar="50M", seq="TTGCA" * 10, qual=[35] * 50, aux=fake + b"\x00" * 7)
+    after = [rec(name=f"b{i}", flag=0x43, ref=1, pos=10 + 9 * i, next_ref=0, next_pos=7, mapq=30, cigar="20M5D30M", seq="GGCAT" * 10, qual=[20] * 50) for i in range(60)]
     # the first record block ends exactly where the decoy starts inside `host`
     cut = sum(len(r[0]) for r in before) + len(host[0]) - len(fake) - 7
     assert cut < 0xFF00
