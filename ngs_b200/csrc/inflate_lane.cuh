@@ -331,7 +331,7 @@ struct Lane {
   // ---- variants 2 / 4: stores under a predicate instead of a branch (device: one @p ST; host: an if) ----
   static NGSQ_HD void store16_if(bool c, uint8_t* p, uint64_t lo, uint64_t hi) {
 #if defined(__CUDA_ARCH__)
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.v4.u32 [%1], {%2, %3, %4, %5};\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %0, 0;\n\tcvta.to.global.u64 a, %1;\n\t@p st.global.v4.u32 [a], {%2, %3, %4, %5};\n\t}"
                  :: "r"((uint32_t)c), "l"(p), "r"((uint32_t)lo), "r"((uint32_t)(lo >> 32)), "r"((uint32_t)hi), "r"((uint32_t)(hi >> 32)) : "memory");
 #else
     if (c) { memcpy(p, &lo, 8); memcpy(p + 8, &hi, 8); }
@@ -339,7 +339,7 @@ struct Lane {
   }
   static NGSQ_HD void store4_if(bool c, uint32_t* p, uint32_t v) {
 #if defined(__CUDA_ARCH__)
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.u32 [%1], %2;\n\t}" :: "r"((uint32_t)c), "l"(p), "r"(v) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %0, 0;\n\tcvta.to.global.u64 a, %1;\n\t@p st.global.u32 [a], %2;\n\t}" :: "r"((uint32_t)c), "l"(p), "r"(v) : "memory");
 #else
     if (c) *p = v;
 #endif
