@@ -320,13 +320,16 @@ struct FacetSet {
   std::vector<std::unique_ptr<RecordBasedQualityControlFacet>> record_based;
   std::vector<std::unique_ptr<SequenceBasedQualityControlFacet>> sequence_based;
 };
-inline FacetSet get_qc_facets(const ReferenceGenome& genome, const std::optional<std::string>& only_facet) {
+inline FacetSet get_qc_facets(const ReferenceGenome& genome, const std::optional<std::string>& only_facet,
+                              std::unique_ptr<GenomicFeaturesFacet> features = nullptr, std::unique_ptr<EditsFacet> edits = nullptr) {
   FacetSet fs;
   fs.record_based.push_back(std::make_unique<GeneralMetricsFacet>());
   fs.record_based.push_back(std::make_unique<TemplateLengthFacet>(TemplateLengthFacet::with_capacity(1024)));
   fs.record_based.push_back(std::make_unique<GCContentFacet>());
   fs.record_based.push_back(std::make_unique<QualityScoreFacet>());
+  if (features) fs.record_based.push_back(std::move(features));  // qc.rs:68-79: after the four defaults
   fs.sequence_based.push_back(std::make_unique<CoverageFacet>(genome, 50000));
+  if (edits) fs.sequence_based.push_back(std::move(edits));      // qc.rs:92-94
   if (only_facet) {
     FacetSet filtered;
     for (auto& f : fs.record_based) if (eq_ignore_ascii_case(f->name(), *only_facet)) filtered.record_based.push_back(std::move(f));

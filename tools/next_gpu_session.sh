@@ -9,7 +9,7 @@ set -u
 mkdir -p gpurun_out
 (timeout 700 python -m pytest tests -m gpu -x -q) > gpurun_out/next_gpu_tests.log 2>&1; tail -2 gpurun_out/next_gpu_tests.log
 (timeout 200 python -c "import __graft_entry__ as g; g.smoke()") > gpurun_out/next_smoke.log 2>&1; tail -1 gpurun_out/next_smoke.log
-for t in decoy edits features; do
+for t in decoy edits features driver_next; do
   (timeout 300 python -m pytest wip/test_gpu_$t.py -x -q) > gpurun_out/next_wip_$t.log 2>&1
   echo "wip $t: $(tail -1 gpurun_out/next_wip_$t.log)"
 done
