@@ -204,6 +204,8 @@ int ngsq_reduce(ngsq_engine* e, int root);
  * ngsq_set_quality_positions with the same value (max over ranks) first. */
 int ngsq_set_quality_positions(ngsq_engine* e, uint32_t n_positions);
 int ngsq_result_buffer(ngsq_engine* e, void** dev_ptr, size_t* n_words);
+/* After an external reduction of that buffer: refresh the host copy the ngsq_get_* getters read. */
+int ngsq_refresh_results(ngsq_engine* e);
 
 /* ---- utilities ---- */
 void* ngsq_host_alloc(size_t nbytes); /* pinned host memory for ngsq_submit */
