@@ -9,7 +9,7 @@ set -u
 mkdir -p gpurun_out
 for pair in "$@"; do
   v=${pair%%:*}; r=${pair##*:}; tag=ab_v${v}_${r}
-  make -C ngs_b200/csrc -B VARIANT=$v RES_VARIANT=$r ../../ngs_b200/libngs_cuda.so > gpurun_out/$tag.log 2>&1 || { echo "$pair: build failed"; continue; }
+  make -C ngs_b200/csrc -B cuda VARIANT=$v RES_VARIANT=$r > gpurun_out/$tag.log 2>&1 || { echo "$pair: build failed"; continue; }
   (timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge.py -m gpu -x -q) >> gpurun_out/$tag.log 2>&1
   tests=$(tail -1 gpurun_out/$tag.log)
   timeout 400 python bench.py --records 30000000 --no-e2e --no-cpu > gpurun_out/$tag.json 2>> gpurun_out/$tag.log
@@ -23,4 +23,4 @@ except Exception as e:
     print("variant %s: no bench line (%s) | %s" % (sys.argv[1], e, sys.argv[3]))
 PY
 done
-make -C ngs_b200/csrc -B VARIANT=0 RES_VARIANT=0 ../../ngs_b200/libngs_cuda.so > /dev/null 2>&1
+make -C ngs_b200/csrc -B cuda VARIANT=0 RES_VARIANT=0 > /dev/null 2>&1
