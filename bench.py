@@ -106,6 +106,48 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+GC_SEED = 7
+
+# name -> (generator shape, records per GPU at N=1, records per GPU at N>1, record facets, coverage)
+# BASELINE.json configs: wgs = configs[1] (N=1, 100 M) / configs[2] (N=8: 600 M = 75 M per GPU); c1 = configs[0];
+# c4 = configs[3] (long reads); c5 = configs[4] (RNA-seq)
+WORKLOADS = {
+    "wgs": (1, 100_000_000, 75_000_000, True, True),
+    "c1": (0, 1_000_000, 1_000_000, True, False),
+    "c4": (2, 2_000_000, 2_000_000, True, True),
+    "c5": (3, 200_000_000, 200_000_000, True, True),
+}
+WORKLOAD_TEXT = {
+    "wgs": "2x150bp WGS-shaped synthetic BAM, all facets incl. coverage",
+    "c1": "2x150bp coordinate-sorted synthetic BAM over a 3-contig reference, record-based facets only",
+    "c4": "long-read (10-50 kb, dense CIGARs) synthetic BAM, all facets incl. coverage",
+    "c5": "spliced 2x100bp RNA-seq-shaped synthetic BAM (CIGAR N skips, high duplicate/secondary rates), all facets incl. coverage",
+}
+
+
+def workload(name, n_ranks, per_gpu=0, level=-1):
+    """The bench workload `name` at n_ranks GPUs: one logical BAM of per_gpu * n_ranks records, cut into
+    contig-exclusive shards (LPT by record count).  Deterministic: tests/golden/make_fullsize_goldens.py builds the
+    goldens from the same description."""
+    from ngs_b200 import ffi
+    shape, one, many, records, coverage = WORKLOADS[name]
+    per_gpu = per_gpu or (one if n_ranks == 1 else many)
+    total = per_gpu * n_ranks
+    if level < 0:
+        # zlib level 1 bounds the generation time of the multi-GB workloads (DESIGN.md section 6); long reads: 56 KB per record
+        level = 1 if per_gpu >= 20_000_000 or shape == 2 else 6
+    per_contig, tail = ffi.synth_layout(shape, total)
+    parts, loads = lpt_partition(per_contig, n_ranks)
+    return {"name": name, "shape": shape, "n_ranks": n_ranks, "per_gpu": per_gpu, "total_records": total, "level": level,
+            "records": records, "coverage": coverage, "parts": parts, "tail_rank": int(np.argmin(loads)),
+            "key": f"{name}_n{n_ranks}_{total}_l{level}"}
+
+
+def workload_shard(wl, rank):
+    """(contig mask, with_tail) of the shard file rank `rank` generates."""
+    return sum(1 << c for c in wl["parts"][rank]), rank == wl["tail_rank"]
+
+
 def lpt_partition(weights, n_parts):
     """Longest-processing-time packing of contigs onto shards (contig-exclusive ownership)."""
     order = sorted(range(len(weights)), key=lambda c: -weights[c])

@@ -18,6 +18,10 @@ constexpr int kCovPerThread = 16;
 constexpr int kCovTile = kCovThreads * kCovPerThread;  // 4096 positions < bin size
 constexpr uint32_t kCovBin = 50000;
 
+// depth -> slot of the CTA-private histogram; [2049] collects depths beyond the reference's 2048 cap.  A negative running depth
+// cannot come from the facet kernel's scatter (+1 at a start precedes its -1); should the int32 array ever wrap, stay in bounds.
+__device__ __forceinline__ uint32_t cov_hist_slot(int64_t d) { return (d > 2048 || d < 0) ? 2049u : (uint32_t)d; }
+
 // tile_sum[t] = sum of diff over tile t  (positions [t*4096, ...) clipped to n = L+1)
 __global__ void __launch_bounds__(kCovThreads)
 cov_tile_sums_kernel(const int32_t* __restrict__ diff, uint32_t n, const uint64_t* __restrict__ touched, int64_t* __restrict__ tile_sum) {
@@ -135,15 +139,20 @@ cov_resolve_kernel(const int32_t* __restrict__ diff, uint32_t n, const int64_t* 
         if (bin == k0) s0 += (unsigned long long)depth; else s1 += (unsigned long long)depth;
         if (depth == run_d) ++run_n;
         else {
-          if (run_n) atomicAdd(&hist[run_d > 2048 ? 2049 : (uint32_t)run_d], run_n);
+          if (run_n) atomicAdd(&hist[cov_hist_slot(run_d)], run_n);
           run_d = depth;
           run_n = 1;
         }
       }
     }
-    if (run_n) atomicAdd(&hist[run_d > 2048 ? 2049 : (uint32_t)run_d], run_n);
-    s0 = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(s0 & 0xFFFFFFFFu)) + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (uint32_t)(s0 >> 32)) << 32);
-    s1 = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(s1 & 0xFFFFFFFFu)) + ((unsigned long long)__reduce_add_sync(0xFFFFFFFFu, (uint32_t)(s1 >> 32)) << 32);
+    if (run_n) atomicAdd(&hist[cov_hist_slot(run_d)], run_n);
+    // 64-bit butterfly: two independent 32-bit reductions of the halves would drop the carry out of the low words once the
+    // 32 lanes' sums pass 2^32 (depth of a few million over the warp's 512 positions: amplicon / rRNA data)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s0 += __shfl_down_sync(0xFFFFFFFFu, s0, o);
+      s1 += __shfl_down_sync(0xFFFFFFFFu, s1, o);
+    }
     if (lane == 0) {
       if (s0) atomicAdd(&bsum[0], s0);
       if (s1) atomicAdd(&bsum[1], s1);

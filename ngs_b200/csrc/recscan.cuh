@@ -126,8 +126,10 @@ __global__ void walk_kernel(const uint8_t* __restrict__ d, const uint64_t* __res
     if (off + 4 + bs > d_end) { if (!EMIT) atomicAdd(&err->truncated, 1u); off = stop; break; }
     if (EMIT) rec[w + n] = ((uint64_t)b << 16) | (off - lo);
     else {
+      // l_seq is not validated yet (the facet kernel does that): only a length the record can hold may size the quality table
       uint32_t lseq = ld_u32_unaligned(d + off + 20);
-      max_lseq = lseq > max_lseq ? lseq : max_lseq;
+      if ((uint64_t)lseq + (lseq + 1ull) / 2 + 32 <= bs) max_lseq = lseq > max_lseq ? lseq : max_lseq;
+      else atomicAdd(&err->bad_record, 1u);
     }
     ++n;
     off += 4 + bs;

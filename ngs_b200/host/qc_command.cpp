@@ -220,11 +220,6 @@ int qc(const QcArgs& args) {
   if (!genome)
     throw std::runtime_error("reference genome is not supported: " + args.reference_genome +
                              ". Did you set the correct reference genome?. Use the `list genomes` subcommand to see supported reference genomes.");
-  // The device paths of these two facets match the oracle in their CPU models but have not been verified on a GPU yet:
-  // refused unless the caller opts in explicitly (used by the parked tests of wip/).
-  const bool unverified_ok = std::getenv("NGS_CUDA_ENABLE_UNVERIFIED_FACETS") != nullptr;
-  if (args.features_gff && !unverified_ok) throw std::runtime_error("--features-gff (Genomic Features facet) is not available on the CUDA engine; run the CPU `ngs qc` for it");
-  if (args.reference_fasta && !unverified_ok) throw std::runtime_error("--reference-fasta (Edits facet) is not available on the CUDA engine; run the CPU `ngs qc` for it");
   if (args.vaf_file_path) throw std::runtime_error("--vaf-file is not available on the CUDA engine (per-position VAFs stay on the device)");
   std::string prefix = args.output_prefix.value_or(std::filesystem::path(args.src).filename().string());
   std::string outdir = args.output_directory.value_or(std::filesystem::current_path().string());

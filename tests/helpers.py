@@ -210,3 +210,88 @@ def canonical_results(path_or_obj):
 def results_digest(path_or_obj) -> str:
     import hashlib
     return hashlib.sha256(json.dumps(canonical_results(path_or_obj), sort_keys=True).encode()).hexdigest()
+
+
+# ---------------------------------------------------------------- full-size goldens (bench.py workloads)
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def merge_ints(parts, records=True, coverage=True):
+    """Sum of the integer dicts of contig-exclusive shards (what ngsq_reduce computes on the device)."""
+    out = {}
+    if records:
+        for k in ["general", "tlen_hist", "gc_hist", "gc_nuc", "gc_rec"]:
+            out[k] = sum(p[k].astype(np.uint64) for p in parts)
+        for k in ["tlen_processed", "tlen_ignored"]:
+            out[k] = int(sum(int(p[k]) for p in parts))
+        rows = max(p["quality"].shape[0] for p in parts)
+        q = np.zeros((rows, 94), dtype=np.uint64)
+        for p in parts:
+            q[: p["quality"].shape[0]] += p["quality"]
+        out["quality"] = q
+    if coverage:
+        cov = {}
+        for p in parts:
+            for c, v in p["coverage"].items():
+                assert c not in cov, f"contig {c} touched by two shards: shards must be contig-exclusive"
+                cov[c] = v
+        out["coverage"] = cov
+        out["nonsensical"] = int(sum(int(p["nonsensical"]) for p in parts))
+    return out
+
+
+def save_fullsize_golden(ints, meta):
+    arrays = {"meta": np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)}
+    for k in ["general", "tlen_hist", "gc_hist", "gc_nuc", "gc_rec", "quality"]:
+        if k in ints:
+            arrays[k] = np.asarray(ints[k], dtype=np.uint64)
+    if "tlen_processed" in ints:
+        arrays["tlen_scalars"] = np.array([ints["tlen_processed"], ints["tlen_ignored"]], dtype=np.uint64)
+    if "coverage" in ints:
+        contigs = sorted(ints["coverage"])
+        arrays["cov_contigs"] = np.array(contigs, dtype=np.int64)
+        arrays["cov_hist"] = np.array([ints["coverage"][c]["hist"] for c in contigs], dtype=np.uint64).reshape(len(contigs), 2049)
+        arrays["cov_too_large"] = np.array([ints["coverage"][c]["too_large"] for c in contigs], dtype=np.uint64)
+        arrays["cov_nbins"] = np.array([len(ints["coverage"][c]["bin_sums"]) for c in contigs], dtype=np.int64)
+        arrays["cov_bins"] = np.concatenate([np.asarray(ints["coverage"][c]["bin_sums"], dtype=np.uint64) for c in contigs]) if contigs else np.zeros(0, np.uint64)
+        arrays["nonsensical"] = np.array([ints["nonsensical"]], dtype=np.uint64)
+    path = os.path.join(GOLDEN_DIR, f"fullsize_{meta['key']}.npz")
+    np.savez_compressed(path, **arrays)
+    return path
+
+
+def load_fullsize_golden(key):
+    """(ints, meta) of tests/golden/fullsize_<key>.npz, or (None, None) when no golden is committed for the workload."""
+    path = os.path.join(GOLDEN_DIR, f"fullsize_{key}.npz")
+    if not os.path.exists(path):
+        return None, None
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    ints = {}
+    for k in ["general", "tlen_hist", "gc_hist", "gc_nuc", "gc_rec", "quality"]:
+        if k in z:
+            ints[k] = z[k]
+    if "tlen_scalars" in z:
+        ints["tlen_processed"], ints["tlen_ignored"] = int(z["tlen_scalars"][0]), int(z["tlen_scalars"][1])
+    if "cov_contigs" in z:
+        cov, o = {}, 0
+        for i, c in enumerate(z["cov_contigs"]):
+            nb = int(z["cov_nbins"][i])
+            cov[int(c)] = {"hist": z["cov_hist"][i], "too_large": int(z["cov_too_large"][i]), "bin_sums": z["cov_bins"][o:o + nb]}
+            o += nb
+        ints["coverage"] = cov
+        ints["nonsensical"] = int(z["nonsensical"][0])
+    return ints, meta
+
+
+def compare_fullsize(got, key, n_records=None):
+    """Compares a run's integers with the committed full-size golden of workload `key`.
+    Returns a one-line verdict; raises AssertionError on any difference."""
+    want, meta = load_fullsize_golden(key)
+    if want is None:
+        return None
+    if n_records is not None:
+        assert int(n_records) == int(meta["records"]), f"records {n_records} != golden {meta['records']}"
+    assert_same_ints(got, want, records="general" in want, coverage="coverage" in want)
+    return (f"bit-exact vs the oracle's integers on the full workload ({meta['records']} records, {meta['n_ranks']} shard file(s); "
+            f"tests/golden/fullsize_{key}.npz)")

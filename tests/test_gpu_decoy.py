@@ -1,11 +1,12 @@
 """Record-boundary scan against a decoy: a BGZF block that BEGINS with bytes that look like three chained BAM records
 (they sit inside another record's auxiliary data).  The speculative first-record search of recscan.cuh must take the
 decoy, the closure check must catch it (the predecessor's walk lands elsewhere), and the serial fallback
-(chain_serial_kernel) must give the oracle's integers.  NOT YET RUN ON A GPU: see wip/README.md.
-Run from the repository root: python -m pytest wip/test_gpu_decoy.py -x -q"""
+(chain_serial_kernel) must give the oracle's integers."""
 import os
 import sys
 import zlib
+
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -44,6 +45,7 @@ def test_the_case_really_puts_the_decoy_at_a_block_start():
     assert blocks[2].startswith(fake)          # block 0 = header, 1 = records up to the decoy, 2 starts with it
 
 
+@pytest.mark.gpu
 def test_decoy_at_a_block_start_is_caught_and_the_results_are_the_oracles():
     bam, bai, _ = _case()
     b, x = as_u8(bam), as_u8(bai)

@@ -1,12 +1,14 @@
-"""The host driver end to end with the two optional facets (opt-in NGS_CUDA_ENABLE_UNVERIFIED_FACETS=1): the `edits` and
-`features` blocks of the results JSON must carry the oracle's integers and the reference's summary arithmetic.
-NOT YET RUN ON A GPU: see wip/README.md.  Run from the repository root: python -m pytest wip/test_gpu_driver_next.py -x -q"""
+"""The host driver end to end with the two optional facets: the `edits` and
+`features` blocks of the results JSON must carry the oracle's integers and the reference's summary arithmetic."""
 import json
 import os
 import subprocess
 import sys
 
 import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -27,9 +29,8 @@ def test_results_json_carries_the_optional_facets(tmp_path):
            + gff_line("chr1", "five_prime_UTR", 200, 260) + gff_line("chr1", "CDS", 261, 700) + gff_line("chr2", "gene", 100, 2500)
            + gff_line("chr2", "three_prime_UTR", 2000, 2500) + gff_line("chrM", "gene", 1, 800))
     (tmp_path / "m.gff").write_text(gff)
-    env = dict(os.environ, NGS_CUDA_ENABLE_UNVERIFIED_FACETS="1")
     r = subprocess.run([EXE, "qc", str(tmp_path / "x.bam"), "GRCh38_no_alt_AnalysisSet", "-o", str(tmp_path), "-p", "out",
-                        "--reference-fasta", str(tmp_path / "ref.fa"), "--features-gff", str(tmp_path / "m.gff")], capture_output=True, text=True, env=env)
+                        "--reference-fasta", str(tmp_path / "ref.fa"), "--features-gff", str(tmp_path / "m.gff")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     doc = json.load(open(tmp_path / "out.results.json"))
     one, two, vaf, n, means = oracle_edits(bam, bai, fa)
@@ -45,9 +46,3 @@ def test_results_json_carries_the_optional_facets(tmp_path):
     assert got == [want[k] for k in KEYS]
     assert (f["summary"]["ignored_flags_pct"], f["summary"]["ignored_nonprimary_chromosome_pct"]) == want["pct"]
     assert doc["general"]["records"]["total"] > 0 and doc["coverage"] is not None   # the default facets ran beside them
-
-
-def test_the_driver_still_refuses_the_flags_without_the_opt_in(tmp_path):
-    r = subprocess.run([EXE, "qc", "x.bam", "GRCh38_no_alt_AnalysisSet", "--reference-fasta", "r.fa"], capture_output=True, text=True,
-                       env={k: v for k, v in os.environ.items() if k != "NGS_CUDA_ENABLE_UNVERIFIED_FACETS"})
-    assert r.returncode == 1 and "not available on the CUDA engine" in r.stderr

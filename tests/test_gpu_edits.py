@@ -1,6 +1,5 @@
 """GPU parity for the Edits facet: every integer `ngsq_get_edits` returns must equal the oracle's
-on the same BAM + FASTA, and the engine must fail where the oracle (the reference) aborts.  NOT YET RUN ON A GPU: see
-wip/README.md.  Run from the repository root: python -m pytest wip/test_gpu_edits.py -x -q"""
+on the same BAM + FASTA, and the engine must fail where the oracle (the reference) aborts."""
 import os
 import sys
 
@@ -10,6 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+pytestmark = pytest.mark.gpu
 
 from bamutil import as_u8, rec, write_bam  # noqa: E402
 from test_edits_model import ERRORS, _one_record_case  # noqa: E402

@@ -1,6 +1,5 @@
 """GPU parity for the Genomic Features facet: the nine counters of `ngsq_get_features` must equal
-the oracle's on the same BAM + GFF, for distinct and coinciding feature names.  NOT YET RUN ON A GPU: see wip/README.md.
-Run from the repository root: python -m pytest wip/test_gpu_features.py -x -q"""
+the oracle's on the same BAM + GFF, for distinct and coinciding feature names."""
 import os
 import random
 import sys
@@ -11,6 +10,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+pytestmark = pytest.mark.gpu
 
 from bamutil import as_u8, write_bam  # noqa: E402
 from test_features_model import NAME_SETS  # noqa: E402

@@ -136,7 +136,10 @@ def make_edits_case(seed=17):
                     seq[k] = str(rng.choice(list("ACGTN")))
             flag = int(rng.choice([0x43, 0x83, 0x63, 0x93, 0x400 | 0x43, 0x4 | 0x41, 0x0, 0x100 | 0x83]))
             recs.append(dict(ref=c, pos=pos, cigar=cig, seq="".join(seq), flag=flag, name=f"r{c}_{i}"))
+    # paired records carry their mate's reference id: the General facet of the reference panics on a mapped pair
+    # without one (general.rs:81-83), and the GPU tests run this case with every facet enabled
     raw = [rec(name=r["name"], flag=r["flag"], ref=r["ref"], pos=r["pos"], mapq=30, cigar=r["cigar"], seq=r["seq"],
+               next_ref=r["ref"] if r["flag"] & 1 else -1, next_pos=r["pos"] if r["flag"] & 1 else -1,
                qual=[30] * len(r["seq"])) for r in recs]
     bam, bai = write_bam(REFS, raw, block_payload=3000)
     fasta = "".join(f">{name} synthetic\n" + "\n".join(s[i:i + 60] for i in range(0, len(s), 60)) + "\n" for name, s in refseqs.items())

@@ -4,7 +4,7 @@
 #   gpurun --timeout 1700 -- 'bash tools/ab_decode.sh 0:0 7:0 15:0 31:0 0:1 31:1'
 # For every pair: rebuild libngs_cuda.so in place, run the inflate / facet parity tests, then a 30 M-record
 # resident-only bench (stage_ms carries the kernels' times).  Results: gpurun_out/ab_v<dec>_<res>.{json,log}.
-# The default library (0:0) is rebuilt at the end.  About 1 GPU-minute of build + 1.5 of run per pair.
+# The default library (Makefile defaults) is rebuilt at the end.  About 1 GPU-minute of build + 1.5 of run per pair.
 set -u
 mkdir -p gpurun_out
 for pair in "$@"; do
@@ -23,4 +23,4 @@ except Exception as e:
     print("variant %s: no bench line (%s) | %s" % (sys.argv[1], e, sys.argv[3]))
 PY
 done
-make -C ngs_b200/csrc -B cuda VARIANT=0 RES_VARIANT=0 > /dev/null 2>&1
+make -C ngs_b200/csrc -B cuda > /dev/null 2>&1
