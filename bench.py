@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """bench.py — `ngs qc` BAM hot path on B200 (BASELINE.json metric: records/s and decompressed GB/s).
 
-A "step" is one full pass of the hot path over one synthetic WGS-shaped BAM shard per GPU:
-BGZF inflate -> record scan -> record facets + coverage scatter -> coverage resolve (-> NCCL merge).
+A "step" is one full pass of the hot path over one synthetic BAM shard per GPU, streamed in waves:
+BGZF inflate -> CRC -> record scan -> record facets + coverage scatter (per wave) -> coverage resolve (-> NCCL merge).
 
   value   device-timed (CUDA events on the engine's stream, max over ranks), compressed BAM
           already resident in HBM when the timed region starts.
   e2e     the same pass through the host-facing C ABI (ngsq_submit from pinned HOST memory in
           chunks, results read back to the host), H2D/D2H inside the timed region, wall clock
           bracketed by barrier + device synchronize.
+  parity  the TIMED runs' own result buffers (last resident step and last e2e step, after the NCCL merge at N>1)
+          are compared with the committed full-size golden of the workload (tests/golden/fullsize_*.npz: the
+          oracle's integers over exactly these shard files); a difference fails the run.
   --impl reference   the CPU oracle (restatement of the reference's single-threaded algorithm;
           the Rust reference cannot be built in this image) on a bounded sample, rank 0 only.
 
-Workload: N=1 -> configs[1] (100M-record 2x150 WGS BAM, all facets incl. coverage).
-N>1 -> one logical 75M*N-record BAM (N=8: configs[2], 600M records) partitioned by contig ranges
-(LPT over record counts); every rank generates exactly its shard, results merged by one NCCL reduce.
+Workloads (--shape): wgs (default) N=1 -> configs[1] (100M-record 2x150 WGS BAM, all facets incl. coverage);
+N>1 -> one logical 75M*N-record BAM (N=8: configs[2], 600M records) partitioned by contig ranges (LPT over
+record counts); every rank generates exactly its shard, results merged by one NCCL all-reduce.
+c1 / c4 / c5 -> configs[0] / [3] / [4] (profiles/ holds their lines; the driver's default run is wgs).
 """
 import argparse
 import ctypes as C
@@ -38,7 +42,8 @@ def parse_args():
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--records", type=int, default=0, help="records per GPU (default 100M at N=1, 75M at N>1)")
+    p.add_argument("--shape", default="wgs", choices=sorted(WORKLOADS), help="workload (BASELINE.json configs): wgs = configs[1]/[2], c1, c4, c5")
+    p.add_argument("--records", type=int, default=0, help="records per GPU (default: the named config's size)")
     p.add_argument("--level", type=int, default=-1, help="zlib level of the synthetic BAM (default 1 for >=20M records, else 6)")
     p.add_argument("--chunk-mb", type=int, default=256, help="e2e submit chunk size")
     p.add_argument("--cpu-sample", type=int, default=3_000_000, help="records in the CPU-baseline sample")
@@ -160,13 +165,14 @@ def lpt_partition(weights, n_parts):
     return parts, loads
 
 
-def cpu_sample(args, total_records, level):
-    """Bounded CPU sample that keeps the workload's SHAPE: whole contigs of the logical `total_records` BAM
-    (same depth, so the per-record and the per-position costs of the reference keep their proportion — a
-    shallow whole-genome sample would charge the reference its 3.1 Gbp coverage sweep for 3 % of the
-    records).  Contigs are taken from the small end until about --cpu-sample records are reached."""
+def cpu_sample(args, wl):
+    """Bounded CPU sample that keeps the workload's SHAPE: whole contigs of the N=1 logical BAM of the shape at full
+    depth (so the per-record and the per-position costs of the reference keep their proportion — a shallow
+    whole-genome sample would charge the reference its 3.1 Gbp coverage sweep for 3 % of the records).  Contigs are
+    taken from the small end until about --cpu-sample records are reached.  The same sample at every N."""
     from ngs_b200 import ffi
-    per_contig, _ = ffi.synth_layout(1, total_records)
+    shape, total, level = wl["shape"], wl["per_gpu"], wl["level"]
+    per_contig, _ = ffi.synth_layout(shape, total)
     order = sorted(range(len(per_contig)), key=lambda c: per_contig[c])
     mask, n = 0, 0
     for c in order:
@@ -174,15 +180,14 @@ def cpu_sample(args, total_records, level):
             continue
         if n >= args.cpu_sample:
             break
-        # once past half the target, do not overshoot it by more than half (the first real contig is always taken:
-        # at 600 M records the smallest chromosome alone holds 9 M)
+        # once past half the target, do not overshoot it by more than half (the first real contig is always taken)
         if n > args.cpu_sample * 0.5 and n + per_contig[c] > args.cpu_sample * 1.5:
             break
         mask |= 1 << c
         n += per_contig[c]
-    bam, bai, info = ffi.synth_bam(1, total_records, level=level, contig_mask=mask, with_tail=False)
+    bam, bai, info = ffi.synth_bam(shape, total, level=level, contig_mask=mask, with_tail=False)
     contigs = [c for c in range(len(per_contig)) if mask >> c & 1]
-    desc = (f"{info['n_records']} records = contigs {contigs} of the {total_records}-record WGS-shaped BAM at full depth "
+    desc = (f"{info['n_records']} records = contigs {contigs} of the {total}-record {wl['name']}-shaped BAM at full depth "
             f"(zlib-{level})")
     return bam, bai, info, desc
 
@@ -192,15 +197,13 @@ def run_reference(args, rank, emit):
     if rank != 0:
         return
     from helpers import oracle_ints
-    from ngs_b200 import ffi
-    total = (args.records or (100_000_000 if args.gpus == 1 else 75_000_000)) * args.gpus  # the logical BAM of the GPU arm
-    level = args.level if args.level >= 0 else (1 if total >= 20_000_000 else 6)
-    bam, bai, info, desc = cpu_sample(args, total, level)
+    wl1 = workload(args.shape, 1, args.records, args.level)
+    bam, bai, info, desc = cpu_sample(args, wl1)
     n = info["n_records"]
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        oracle_ints(bam, bai, gc_seed=7)
+        oracle_ints(bam, bai, gc_seed=GC_SEED, records=wl1["records"], coverage=wl1["coverage"])
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
@@ -208,14 +211,15 @@ def run_reference(args, rank, emit):
             break
     per = float(np.mean(times))
     val = n / per
+    passes = int(wl1["records"]) + int(wl1["coverage"])
     line = {
         "impl": "reference", "metric": "ngs qc records/sec", "value": val, "unit": "records/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u64", "data": "synthetic",
-        "decompressed_gbs": info["inflated_bytes"] * 2 / per / 1e9,
-        "config": {"workload": "WGS-shaped 2x150 synthetic BAM, all facets incl. coverage (bounded sample of configs[1]: " + desc + ")",
-                   "sample_records": n, "note": "CPU restatement of the reference (oracle/ngsqc_oracle.c, zlib inflate, two passes, 1 thread); the Rust reference cannot be built in this image"},
-        "cpu_baseline": {"value": val, "unit": "records/s", "cores": 1, "kind": "port", "sample": desc + ", both passes"},
+        "decompressed_gbs": info["inflated_bytes"] * passes / per / 1e9,
+        "config": {"workload": f"{WORKLOAD_TEXT[args.shape]} (bounded sample of the named config: {desc})",
+                   "sample_records": n, "note": "CPU restatement of the reference (oracle/ngsqc_oracle.c, zlib inflate, one pass per facet family, 1 thread: the reference's qc path is single-threaded); the Rust reference cannot be built in this image"},
+        "cpu_baseline": {"value": val, "unit": "records/s", "cores": 1, "kind": "port", "sample": desc + f", {passes} pass(es)"},
         "e2e": {"value": val, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -227,6 +231,26 @@ _T0 = time.perf_counter()
 def log(msg):
     """Progress on stderr (stdout carries only the JSON line): makes a hang on a GPU box diagnosable."""
     print(f"[bench r{os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pins this process to the CPUs of the GPU's NUMA node before any pinned allocation (first touch decides where the
+    staging memory lives).  Returns a short description for the JSON line."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)], capture_output=True, text=True).stdout.strip()
+        bdf = out.lower().replace("00000000:", "0000:") if out else None
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read()) if bdf else -1
+        if node < 0:
+            return {"numa_node": node, "bound": False}
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, ids & os.sched_getaffinity(0) or os.sched_getaffinity(0))
+        return {"numa_node": node, "bound": True, "cpus": cpus}
+    except Exception as ex:  # never fail the bench over a binding
+        return {"numa_node": None, "bound": False, "error": str(ex)[:80]}
 
 
 def main():
@@ -252,13 +276,14 @@ def main():
     import torch
     import torch.distributed as dist
     from ngs_b200 import ffi, formats
-    from helpers import assert_same_ints, collect, engine_ints, oracle_ints
+    from helpers import assert_same_ints, collect, compare_fullsize, engine_ints, oracle_ints
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the ngs-cuda engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     N = args.gpus
+    numa = bind_to_gpu_numa_node(local_rank)
     if N > 1:
         log("init_process_group")
         dist.init_process_group("nccl", device_id=dev)
@@ -268,18 +293,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    per_gpu = args.records or (100_000_000 if N == 1 else 75_000_000)
-    total_records = per_gpu * N
-    level = args.level if args.level >= 0 else (1 if per_gpu >= 20_000_000 else 6)
-    shape = 1
+    wl = workload(args.shape, N, args.records, args.level)
+    shape, level, total_records = wl["shape"], wl["level"], wl["total_records"]
+    named = args.records == 0 and args.level < 0  # the size BASELINE.json names for this shape
 
     # ---- this rank's shard of the logical BAM (contig-exclusive, LPT by record count) ----
-    per_contig, tail = ffi.synth_layout(shape, total_records)
-    parts, loads = lpt_partition(per_contig, N)
-    tail_rank = int(np.argmin(loads))
-    mask = sum(1 << c for c in parts[rank])
+    mask, with_tail = workload_shard(wl, rank)
     t0 = time.perf_counter()
-    bam, bai, info = ffi.synth_bam(shape, total_records, level=level, contig_mask=mask, with_tail=(rank == tail_rank))
+    bam, bai, info = ffi.synth_bam(shape, total_records, level=level, contig_mask=mask, with_tail=with_tail)
     gen_s = time.perf_counter() - t0
     log(f"generated shard: {info['n_records']} records, {bam.size} bytes in {gen_s:.1f}s")
     n_rec = info["n_records"]
@@ -295,8 +316,11 @@ def main():
     del bam
     blocks, n_blocks, used = ffi.bgzf_walk(pinned)
     assert used == C_bytes
-    flags = ffi.NGSQ_F_RECORD_FACETS | ffi.NGSQ_F_COVERAGE | (0 if args.no_crc else ffi.NGSQ_F_VERIFY_CRC)
-    eng = ffi.Engine(device=local_rank, flags=flags, gc_seed=7, reserve_compressed=C_bytes, reserve_inflated=D_bytes + 65536,
+    flags = ((ffi.NGSQ_F_RECORD_FACETS if wl["records"] else 0) | (ffi.NGSQ_F_COVERAGE if wl["coverage"] else 0)
+             | (0 if args.no_crc else ffi.NGSQ_F_VERIFY_CRC))
+    # the engine streams: two wave slots of inflated bytes whatever the file size; the compressed shard stays resident
+    # here because the device-timed `value` needs it in HBM when the timed region starts
+    eng = ffi.Engine(device=local_rank, flags=flags, gc_seed=GC_SEED, reserve_compressed=C_bytes, reserve_inflated=D_bytes + 65536,
                      reserve_blocks=n_blocks + 16)
     hdr = formats.read_header(eng, pinned)
     names = [n for n, _ in hdr.refs]
@@ -345,8 +369,7 @@ def main():
         eng.finish()
         if N > 1:
             eng.reduce(0)
-        res = collect(eng, lens, enabled)  # D2H of every result the host consumes
-        return res
+        return collect(eng, lens, enabled, wl["records"], wl["coverage"])  # D2H of every result the host consumes
 
     # ---- warm-up ----
     for i in range(max(args.warmup, 3)):
@@ -357,10 +380,12 @@ def main():
     sampler.start()
     barrier()
     t0 = time.perf_counter()
-    dev_ms, infl_ms, dec_ms_l, res_ms_l, stats = [], [], [], [], None
+    dev_ms, red_ms, tot_ms, infl_ms, dec_ms_l, res_ms_l, stats = [], [], [], [], [], [], None
     for _ in range(args.steps):
         stats = step_resident()
         dev_ms.append(stats["ms_total"] + stats["ms_reduce"])
+        red_ms.append(stats["ms_reduce"])
+        tot_ms.append(stats["ms_total"])
         infl_ms.append(stats["ms_inflate"])
         dec_ms_l.append(stats["ms_inflate_decode"])
         res_ms_l.append(stats["ms_inflate_resolve"])
@@ -368,78 +393,122 @@ def main():
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop()
     dev_step_ms = float(np.mean(dev_ms))
+    res_resident = collect(eng, lens, enabled, wl["records"], wl["coverage"])  # the last TIMED step's own results
 
     # ---- timed: end to end from pinned host memory ----
     log(f"resident steps done: {dev_step_ms:.1f} ms/step")
     e2e_ms = None
-    res = None
+    res_e2e = None
+    e2e_tail = None
+    h2d_gbs = None
     if not args.no_e2e:
         step_e2e()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            res = step_e2e()
+            res_e2e = step_e2e()
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e_tail = res_e2e["stats"]["ms_tail"]
+        # the box's host-to-device ceiling with all ranks copying at once: the same pinned buffer, the same chunks,
+        # no kernels — what an e2e step could reach if the GPU work were free
+        scratch = torch.empty(min(C_bytes, 4 << 30) + 512, dtype=torch.uint8, device=dev)
+        src = torch.from_numpy(pinned[: scratch.numel() - 512])
+        scratch[: src.numel()].copy_(src, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            scratch[: src.numel()].copy_(src, non_blocking=True)
+        barrier()
+        h2d_gbs = 2 * src.numel() / (time.perf_counter() - t0) / 1e9
+        del scratch
 
     log("e2e steps done")
     # ---- max over ranks ----
-    agg = torch.tensor([dev_step_ms, wall_ms, e2e_ms or 0.0, float(np.mean(infl_ms))], dtype=torch.float64, device=dev)
-    tot = torch.tensor([n_rec, C_bytes, D_bytes], dtype=torch.float64, device=dev)
+    agg = torch.tensor([dev_step_ms, wall_ms, e2e_ms or 0.0, float(np.mean(infl_ms)), float(np.mean(tot_ms)), -float(np.mean(tot_ms)),
+                        float(np.mean(red_ms)), -(h2d_gbs or 0.0), e2e_tail or 0.0], dtype=torch.float64, device=dev)
+    tot = torch.tensor([n_rec, C_bytes, D_bytes, stats["records"], (res_e2e or res_resident)["stats"]["records"]], dtype=torch.float64, device=dev)
     if N > 1:
         dist.all_reduce(agg, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_step_ms, wall_ms, e2e_ms_max, infl_ms_max = [float(x) for x in agg.cpu()]
-    all_rec, all_C, all_D = [float(x) for x in tot.cpu()]
+    dev_step_ms, wall_ms, e2e_ms_max, infl_ms_max, tot_ms_max, neg_tot_ms_min, red_ms_max, neg_h2d_min, e2e_tail_max = [float(x) for x in agg.cpu()]
+    all_rec, all_C, all_D, got_rec_resident, got_rec_e2e = [float(x) for x in tot.cpu()]
 
-    # ---- parity + CPU baseline on a bounded sample (rank 0) ----
-    cpu = None
+    # ---- parity of the TIMED runs against the committed full-size golden (rank 0 holds the merged integers) ----
     parity = None
+    parity_failed = None
+    if rank == 0:
+        try:
+            verdicts = []
+            for label, res, got_rec in (("resident", res_resident, got_rec_resident), ("e2e", res_e2e, got_rec_e2e)):
+                if res is None:
+                    continue
+                assert int(got_rec) == int(all_rec), f"{label}: engine counted {int(got_rec)} records, the generator wrote {int(all_rec)}"
+                v = compare_fullsize(res, wl["key"], n_records=all_rec)
+                verdicts.append((label, v))
+            if verdicts and all(v for _, v in verdicts):
+                parity = "timed " + " and ".join(l for l, _ in verdicts) + " runs: " + verdicts[0][1]
+            else:
+                parity = (f"record counts of the timed runs equal the generator's ({int(all_rec)}); no full-size golden committed for {wl['key']} "
+                          "(sample parity below)")
+        except AssertionError as ex:
+            parity_failed = "FAILED: " + " ".join(str(ex).split())[:300]
+            parity = parity_failed
+
+    # ---- N-rank parity on ONE file: BAI-derived shards + the engine's NCCL merge vs the oracle's whole-file integers ----
+    cpu = None
+    sample_parity = None
     merged_parity = None
     if N > 1 and not args.no_cpu:
-        # N-rank parity: the same contig-exclusive partition + the engine's NCCL reduce on a small logical
-        # BAM must reproduce the oracle's whole-file integers (coverage included) on rank 0
         sn = args.cpu_sample
-        per_s, _ = ffi.synth_layout(shape, sn)
-        parts_s, loads_s = lpt_partition(per_s, N)
-        mask_s = sum(1 << c for c in parts_s[rank])
-        sb, _, _ = ffi.synth_bam(shape, sn, level=6, contig_mask=mask_s, with_tail=(rank == int(np.argmin(loads_s))))
+        sb, sbai, _ = ffi.synth_bam(shape, sn, level=6)      # every rank writes the same bytes (deterministic generator)
         hdr_s = formats.read_header(eng, sb)
+        sblocks, sn_blocks, _ = ffi.bgzf_walk(sb)
+        shards = formats.plan_shards(hdr_s, formats.parse_bai(sbai.tobytes()), N, sb.size)
+        sh = shards[rank]
         eng.reset()
-        eng.set_range(hdr_s.first_voffset, 0)
-        eng.submit(sb, 0)
+        if sh.contigs:
+            lo, hi = formats.shard_byte_range(sh, sblocks, sn_blocks, sb.size)
+            eng.set_range(sh.first_voffset, sh.end_voffset)
+            eng.submit(np.ascontiguousarray(sb[lo:hi]), lo)
+        else:
+            eng.set_range(0, 0)
         eng.finish()
         eng.reduce(0)
         if rank == 0:
             try:
-                got_m = collect(eng, lens, enabled)
-                wb, wbai, _ = ffi.synth_bam(shape, sn, level=6)
-                # every rank wrote its own shard file, so records sit at other virtual offsets than in the
-                # whole file and the GC window offsets differ: compare the GC fields that do not depend on it
-                assert_same_ints(got_m, oracle_ints(wb, wbai, gc_seed=7), gc_window=False)
-                merged_parity = (f"{N}-rank shards + NCCL reduce bit-exact vs oracle on the whole {sn}-record sample "
-                                 "(GC window histogram: invariants only, shard files have their own virtual offsets)")
+                got_m = collect(eng, lens, enabled, wl["records"], wl["coverage"])
+                assert_same_ints(got_m, oracle_ints(sb, sbai, gc_seed=GC_SEED, records=wl["records"], coverage=wl["coverage"]),
+                                 records=wl["records"], coverage=wl["coverage"], gc_window=True)
+                cut_inside = sum(1 for s in shards if s.end_voffset & 0xFFFF)
+                merged_parity = (f"ONE {sn}-record file cut into {N} BAI-derived shards ({cut_inside} cuts inside a BGZF block), one shard per rank, "
+                                 "engine NCCL merge: bit-exact vs the oracle on the whole file, GC window histogram included")
             except AssertionError as ex:  # never leave the other ranks waiting
-                merged_parity = "FAILED: " + str(ex).strip().splitlines()[-1][:200]
+                merged_parity = "FAILED: " + " ".join(str(ex).split())[:300]
+        eng.reset()
+        eng.set_range(hdr.first_voffset, 0)
         log("merged parity checked")
     if rank == 0 and not args.no_cpu:
-        sbam, sbai, sinfo, sdesc = cpu_sample(args, total_records, level)
+        wl1 = workload(args.shape, 1, args.records, args.level)
+        sbam, sbai, sinfo, sdesc = cpu_sample(args, wl1)
         sn = sinfo["n_records"]
         t0 = time.perf_counter()
-        want = oracle_ints(sbam, sbai, gc_seed=7)
+        want = oracle_ints(sbam, sbai, gc_seed=GC_SEED, records=wl["records"], coverage=wl["coverage"])
         cpu_s = time.perf_counter() - t0
-        got = engine_ints(sbam, gc_seed=7, device=local_rank)
-        assert_same_ints(got, want)
-        parity = "bit-exact vs oracle on the CPU-baseline sample (all integer outputs)"
+        got = engine_ints(sbam, gc_seed=GC_SEED, device=local_rank, records=wl["records"], coverage=wl["coverage"])
+        try:
+            assert_same_ints(got, want, records=wl["records"], coverage=wl["coverage"])
+            sample_parity = "bit-exact vs oracle on the CPU-baseline sample (all integer outputs)"
+        except AssertionError as ex:
+            sample_parity = "FAILED: " + " ".join(str(ex).split())[:300]
         cpu = {"value": sn / cpu_s, "unit": "records/s", "cores": 1, "kind": "port",
-               "sample": f"{sdesc}, both passes, {cpu_s:.1f} s; host has {os.cpu_count()} cores, the reference qc path uses 1"}
+               "sample": f"{sdesc}, {int(wl['records']) + int(wl['coverage'])} pass(es), {cpu_s:.1f} s; host has {os.cpu_count()} cores, the reference qc path uses 1"}
 
     if rank == 0:
         peak, peak_kind = measured_peak()
         launches = max(stats["inflate_launches"], 1)
         dec_ms = float(np.mean(dec_ms_l)) / launches   # average launch duration of the dominant kernel (CUDA events)
         res_ms = float(np.mean(res_ms_l)) / launches
-        infl_launch_ms = infl_ms_max / launches
         # algorithmic bytes of the decode kernel per launch: compressed bytes read + inflated bytes written
         # (every 16-byte chunk is written once: literals, in-place match tokens, zeros elsewhere)
         achieved = (C_bytes + D_bytes) / launches / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
@@ -451,7 +520,9 @@ def main():
                 traffic = tj["decode_dram_bytes_per_inflated_byte"] * D_bytes / launches
         except Exception:
             pass
-        A = all_C + 2 * all_D + sum(8 * (L + 2) for c, L in enumerate(lens) if formats.is_primary(names[c]))
+        cov_bytes = sum(8 * (L + 2) for c, L in enumerate(lens) if enabled[c]) if wl["coverage"] else 0
+        A = all_C + 2 * all_D + cov_bytes
+        config_name = {"wgs": "configs[1]" if N == 1 else ("configs[2]" if N == 8 else "configs[1]/[2] family"), "c1": "configs[0]", "c4": "configs[3]", "c5": "configs[4]"}[args.shape]
         line = {
             "metric": "ngs qc records/sec", "value": all_rec / (dev_step_ms * 1e-3), "unit": "records/s", "n_gpus": N,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_step_ms, "higher_is_better": True,
@@ -459,33 +530,41 @@ def main():
             "decompressed_gbs": all_D / (dev_step_ms * 1e-3) / 1e9,
             "pipeline_hbm_frac": A / (dev_step_ms * 1e-3) / 1e9 / (peak * N),
             "wall_ms_per_step": wall_ms,
-            "config": {"workload": ("configs[1]: 100M-record 2x150bp WGS-shaped synthetic BAM, all facets incl. coverage" if N == 1 and per_gpu == 100_000_000
-                                    else f"{int(all_rec)}-record 2x150bp WGS-shaped synthetic BAM partitioned by contig ranges over {N} GPU(s), all facets incl. coverage"),
+            "config": {"workload": (f"{config_name}: {int(all_rec)}-record {WORKLOAD_TEXT[args.shape]}" if named else
+                                    f"{int(all_rec)}-record {WORKLOAD_TEXT[args.shape]} (NOT the named size of {config_name})")
+                                   + (f", partitioned by contig ranges over {N} GPUs ({wl['per_gpu']} records per GPU; N=1 runs configs[1] = 100 M per GPU)" if N > 1 else ""),
                        "records": int(all_rec), "compressed_bytes": int(all_C), "inflated_bytes": int(all_D), "zlib_level": level,
-                       "crc_check": not args.no_crc,
+                       "crc_check": not args.no_crc, "waves_per_gpu": int(stats["waves"]),
                        "l2": "inputs (GBs) far exceed the 126 MB L2; no flush needed", "generation_s": gen_s,
-                       "stage_ms": {k: stats[k] for k in ["ms_inflate", "ms_inflate_decode", "ms_inflate_resolve", "ms_crc", "ms_scan", "ms_facets", "ms_coverage"]},
+                       "stage_ms": {k: stats[k] for k in ["ms_inflate", "ms_inflate_decode", "ms_inflate_resolve", "ms_crc", "ms_scan", "ms_facets", "ms_coverage", "ms_tail"]},
+                       "ms_reduce": red_ms_max, "rank_ms_total": {"max": tot_ms_max, "min": -neg_tot_ms_min},
                        "stage_gbs": {"inflate (C+D)/t": (C_bytes + D_bytes) / (stats["ms_inflate"] * 1e-3) / 1e9 if stats["ms_inflate"] else None,
                                      "resolve D/t": D_bytes / (res_ms * launches * 1e-3) / 1e9 if res_ms else None,
                                      "crc D/t": D_bytes / (stats["ms_crc"] * 1e-3) / 1e9 if stats["ms_crc"] else None,
                                      "scan+facets D/t": D_bytes / ((stats["ms_scan"] + stats["ms_facets"]) * 1e-3) / 1e9,
-                                     "coverage 8*sum(L)/t": sum(8 * (L + 2) for c, L in enumerate(lens) if enabled[c]) / (stats["ms_coverage"] * 1e-3) / 1e9 if stats["ms_coverage"] else None}},
+                                     "coverage 8*sum(L)/t": cov_bytes / (stats["ms_coverage"] * 1e-3) / 1e9 if stats["ms_coverage"] and cov_bytes else None}},
             "roofline": {"bound": "hbm", "kernel": "inflate_decode_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_kind": peak_kind,
-                         "launch_ms": dec_ms,
+                         "launch_ms": dec_ms, "launches_per_step": launches,
                          "note": "algorithmic bytes = compressed read + inflated written per launch; Huffman decode is instruction-issue bound, not HBM-bound (DESIGN.md section 4)"},
             "cpu_baseline": cpu,
             "e2e": None if args.no_e2e else {"value": all_rec / (e2e_ms_max * 1e-3), "unit": "records/s", "h2d_bytes_per_step": int(all_C),
-                                             "d2h_bytes_per_step": int(8 * (1184 + 94 * 256 + sum(2052 + L // 50000 + 2 for L in lens))), "ms_per_step": e2e_ms_max},
+                                             "d2h_bytes_per_step": int(8 * (1216 + 94 * 256 + sum(2052 + L // 50000 + 2 for L in lens))), "ms_per_step": e2e_ms_max,
+                                             "ms_tail_after_last_wave_starts": e2e_tail_max,
+                                             "h2d_ceiling_gbs_per_gpu": -neg_h2d_min,
+                                             "h2d_ceiling_ms": (C_bytes / 1e9) / (-neg_h2d_min) * 1e3 if neg_h2d_min else None,
+                                             "frac_of_h2d_ceiling": ((C_bytes / 1e9) / (-neg_h2d_min) * 1e3) / e2e_ms_max if neg_h2d_min else None,
+                                             "numa": numa},
             "gpu_launches": int((stats["inflate_launches"] + stats["other_launches"]) * args.steps),
-            "clocks": clocks, "parity": parity, "merged_parity": merged_parity,
+            "clocks": clocks, "parity": parity, "sample_parity": sample_parity, "merged_parity": merged_parity,
         }
         emit(line)
     lib.ngsq_host_free(pin_ptr)
     if N > 1:
         dist.destroy_process_group()
-    if merged_parity and merged_parity.startswith("FAILED"):
-        raise SystemExit("merged parity check failed: " + merged_parity)
+    for v in (parity_failed, merged_parity, sample_parity):
+        if v and v.startswith("FAILED"):
+            raise SystemExit("parity check failed: " + v)
 
 
 if __name__ == "__main__":

@@ -53,16 +53,16 @@ enum {
   NGSQ_E_NCCL = -9,
   NGSQ_E_NOMEM = -10,
   NGSQ_E_EDITS = -11,     /* the Edits facet met a record / reference the reference program aborts on */
-  NGSQ_E_FEATURES = -12   /* likewise for the Genomic Features facet */
+  NGSQ_E_FEATURES = -12,  /* likewise for the Genomic Features facet */
+  NGSQ_E_QUAL_CAP = -13   /* a read is longer than the quality table: raise quality_positions and run again */
 };
 
 /* ngsq_config.flags */
 #define NGSQ_F_RECORD_FACETS 1u /* General, Template Length, GC Content, Quality Score */
 #define NGSQ_F_COVERAGE 2u      /* Coverage */
 #define NGSQ_F_VERIFY_CRC 4u    /* verify the CRC32 of every block (reference behaviour) */
-#define NGSQ_F_EDITS 8u         /* Edits (needs ngsq_set_reference_bases for every contig that holds records);
-                                   written against the oracle and a host model, not yet measured on a GPU */
-#define NGSQ_F_FEATURES 16u     /* Genomic Features (needs ngsq_set_feature_model + ngsq_set_features); same status */
+#define NGSQ_F_EDITS 8u         /* Edits (needs ngsq_set_reference_bases for every contig that holds records) */
+#define NGSQ_F_FEATURES 16u     /* Genomic Features (needs ngsq_set_feature_model + ngsq_set_features) */
 
 typedef struct ngsq_engine ngsq_engine;
 
@@ -70,12 +70,18 @@ typedef struct ngsq_config {
   uint32_t struct_size;        /* sizeof(ngsq_config) */
   uint32_t flags;              /* NGSQ_F_* */
   uint64_t gc_seed;            /* GC window policy: see ngsq_get_gc */
-  uint64_t max_records;        /* `-n`: first N records in file order; 0 = all */
-  uint64_t reserve_compressed; /* optional upper bounds; 0 = grow on demand */
-  uint64_t reserve_inflated;
-  uint32_t reserve_blocks;
-  uint32_t launch_blocks;      /* tuning/testing: BGZF blocks per inflate launch of ngsq_submit; 0 = one wave of the
-                                  decode kernel (one block per lane, SMs x 544 lanes) */
+  uint64_t max_records;        /* `-n` (command.rs:305-316 and :384-388): pass 1 takes the first N records in file order;
+                                  pass 2 (Coverage) applies the reference's shared counter: the first N records its
+                                  per-contig queries yield, then the first yielded record of every later contig; 0 = all */
+  uint64_t reserve_compressed; /* optional: size of the whole compressed shard.  Set -> it stays resident in one device
+                                  buffer; 0 -> a staging ring of comp_ring_bytes that is recycled wave by wave */
+  uint64_t reserve_inflated;   /* optional: inflated size of the shard (sizes the two wave slots once) */
+  uint32_t reserve_blocks;     /* optional: BGZF blocks of the shard (equal waves, a small last wave) */
+  uint32_t launch_blocks;      /* tuning/testing: BGZF blocks per wave; 0 = one block per lane of the decode kernel
+                                  (SMs x 576 lanes) */
+  uint32_t quality_positions;  /* rows of the quality-by-position table = longest read the run may hold; 0 = 131072 */
+  uint32_t carry_bytes;        /* longest record that may straddle two waves; 0 = 16 MiB */
+  uint64_t comp_ring_bytes;    /* device bytes of the compressed staging ring when reserve_compressed is 0; 0 = 8 GiB */
 } ngsq_config;
 
 /* One BGZF block as framed by the host (K1). */
@@ -103,7 +109,9 @@ typedef struct ngsq_stats {
   float ms_inflate_decode;   /* of ms_inflate: the lane-per-block Huffman decode kernel */
   float ms_inflate_resolve;  /* of ms_inflate: the warp-per-block LZ77 resolve kernel */
   float ms_reduce;           /* ngsq_reduce: agreement all-reduce + sum-reduce + refresh (0 without it) */
-  float ms_edits;            /* Edits kernel + VAF histogram (0 without NGSQ_F_EDITS) */
+  float ms_edits;            /* VAF histogram of the Edits facet (its per-record kernel runs inside ms_facets) */
+  float ms_tail;             /* start of the LAST wave -> end of finish: what is left once the last chunk has arrived */
+  uint32_t waves;            /* inflate waves of the run (= inflate_launches) */
 } ngsq_stats;
 
 int ngsq_version(void);
@@ -149,18 +157,28 @@ int ngsq_set_range(ngsq_engine* e, uint64_t first_rec_voffset, uint64_t end_voff
 int ngsq_bgzf_walk(const uint8_t* bgzf, size_t nbytes, uint64_t file_off, ngsq_block* out, uint32_t cap,
                    uint32_t* n_blocks, size_t* consumed);
 
-/* Streams one chunk of whole BGZF blocks from HOST memory: async H2D copy; the inflate kernels are
- * launched whenever launch_blocks blocks have been copied (and by ngsq_finish for the rest), so the
- * copy of one chunk overlaps the kernels of the previous ones.  The buffer must stay valid until
- * ngsq_finish returns.  Chunks must be submitted in file order. */
+/* Streams one chunk of whole BGZF blocks from HOST memory: async H2D copy into the staging ring; a WAVE (inflate ->
+ * CRC -> record scan -> facet kernels) is enqueued whenever launch_blocks blocks have been copied (and by ngsq_finish
+ * for the rest), so the copy of one chunk overlaps the kernels of the previous ones and the device footprint does not
+ * grow with the file.  The call never waits for the GPU unless the ring is full.  The buffer must stay valid until its
+ * copy has completed (ngsq_wait_copied, or ngsq_finish).  Chunks must be submitted in file order; ngsq_set_range first. */
 int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t file_off);
+/* Enqueues a wave for every block submitted so far instead of waiting for a full one.  A caller that knows its last
+ * chunk calls this just before submitting it: what remains after the last copied byte is then one small wave. */
+int ngsq_flush(ngsq_engine* e);
+/* Records whose wave has been scanned so far (never blocks; lags the submits by about one wave): the caller's
+ * RecordCounter log line, src/utils/display.rs:43-52. */
+int ngsq_progress(ngsq_engine* e, uint64_t* records);
+/* Blocks until the host buffer of this run's submit_index-th ngsq_submit (0-based) has been copied to the device:
+ * the caller may then refill it (pinned double-buffered file readers). */
+int ngsq_wait_copied(ngsq_engine* e, uint32_t submit_index);
 /* Same for a chunk already resident in DEVICE memory (used in place, not copied); the caller
  * passes the descriptors ngsq_bgzf_walk produced for it.  The allocation must stay readable for 64 bytes
  * past nbytes: the decoders read their input through aligned 8-byte windows that run ahead of the last
  * block's end (ngsq_submit pads its own copies). */
 int ngsq_submit_device(ngsq_engine* e, const void* dev_bgzf, size_t nbytes, const ngsq_block* blocks, uint32_t n_blocks);
 
-/* Record-boundary scan, facet kernels, coverage resolve; blocks until the device is done. */
+/* Last wave, coverage resolve, result read-back; blocks until the device is done. */
 int ngsq_finish(ngsq_engine* e);
 
 /* ---- integer results (valid after ngsq_finish / ngsq_reduce) ---- */
@@ -210,6 +228,9 @@ int ngsq_refresh_results(ngsq_engine* e);
 /* ---- utilities ---- */
 void* ngsq_host_alloc(size_t nbytes); /* pinned host memory for ngsq_submit */
 void ngsq_host_free(void* p);
+/* Page-locks a range the caller already owns (e.g. a mapped file) so that ngsq_submit copies from it asynchronously. */
+int ngsq_host_register(void* p, size_t nbytes);
+int ngsq_host_unregister(void* p);
 /* GPU-inflates whole BGZF blocks and copies the bytes back (header parsing on the host). */
 int ngsq_inflate_to_host(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint8_t* out, size_t cap, size_t* n_out);
 

@@ -3,9 +3,9 @@
 // base differs from the reference FASTA base, per reference position the counts of matching / differing reads,
 // and at the end of the run the histogram of per-position variant allele fractions.
 //
-// STATUS: written against the oracle (oracle/ngsqc_oracle.c, "Edits") with its per-record logic shared with a
-// host model (tools/edits_model.cpp, tests/test_edits_model.py); the CUDA wrappers below have NOT run on a GPU
-// yet (no GPU time was left in the round that wrote them).  Nothing launches them unless NGSQ_F_EDITS is set.
+// Written against the oracle (oracle/ngsqc_oracle.c, "Edits"); the per-record logic is shared with a host model
+// (tools/edits_model.cpp, tests/test_edits_model.py); GPU parity: tests/test_gpu_edits.py.  Launched per wave when
+// NGSQ_F_EDITS is set.
 //
 // Layout in HBM (per contig with a loaded sequence):
 //   codes      (one allocation per contig) 1 byte per FASTA base: the BAM 4-bit code of the letter (index in "=ACMGRSVTWYHKDBN"), 0xFF for a
@@ -18,6 +18,10 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+
+#if defined(__CUDACC__)
+#include "recscan.cuh"
+#endif
 
 #ifndef NGSQ_HD
 #if defined(__CUDACC__)
@@ -184,10 +188,9 @@ NGSQ_HD uint32_t edits_vaf_bin(uint32_t refs, uint32_t alts) {
 #if defined(__CUDACC__)
 
 struct EditsParams {
-  const uint8_t* d;            // inflated stream
-  const uint64_t* rec;         // record table: (block << 16) | offset in block
-  uint64_t n_rec;
-  const uint64_t* out_off;
+  const uint8_t* d;            // base of the wave's slot
+  const uint64_t* rec;         // record table of the wave (recscan.cuh): slot offset in the low 40 bits
+  const RunState* st;          // wave_rec, fatal
   int32_t n_ref;
   const EditsContig* contigs;
   uint32_t* refs;
@@ -200,9 +203,9 @@ __global__ void __launch_bounds__(256) edits_kernel(EditsParams P) {
   for (uint32_t i = threadIdx.x; i < 128; i += blockDim.x) (&s_hist[0][0])[i] = 0;
   __syncthreads();
   uint32_t n_counted = 0, err = 0;
-  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n_rec; r += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t rv = P.rec[r];
-    const uint8_t* rec = P.d + P.out_off[rv >> 16] + (rv & 0xFFFF);
+  const uint64_t n_rec = P.st->fatal ? 0 : P.st->wave_rec;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t* rec = P.d + (P.rec[r] & kRecOffMask);
     const int32_t ref = (int32_t)ed_ld32(rec + 4);
     uint32_t* refs = P.refs;
     uint32_t* alts = P.alts;

@@ -1,11 +1,14 @@
 // libngs_cuda.so — implementation of include/ngs_cuda.h.
-// One engine = one GPU = one host thread.  Device-resident layout (sized for 180 GB HBM3e):
-//   compressed BGZF bytes | inflated byte stream (contiguous, blocks at ISIZE prefix sums)
-//   | block tables | record offset table (8 B/record) | per-contig int32 difference arrays
-//   | packed u64 result buffer (the NCCL reduce payload).
-// Streams: H2D copies on s_copy, kernels on s_comp, the per-block CRC32 check on s_aux (it depends only on the
-// inflated bytes, so it runs beside the record scan and the facet kernel); each submitted chunk's inflate launch waits
-// only for its own copy, so PCIe transfer of chunk k+1 overlaps inflate of chunk k.
+// One engine = one GPU = one host thread.  The file is STREAMED: blocks are inflated in waves (one launch of the
+// decode kernel each) into two recycled slots, and every wave's records are scanned and tallied before its slot is
+// reused, so the device footprint does not grow with the file (30x WGS, 270 GB inflated, runs in a few GB):
+//   compressed staging ring | 2 x [headroom | one wave of inflated bytes] | match bitmap of a wave | per-wave block
+//   tables | record offset table of a wave (8 B/record) | per-contig int32 difference arrays | packed u64 result
+//   buffer (the NCCL payload) | RunState (everything that links two waves, recscan.cuh).
+// Streams: H2D copies on s_copy, kernels on s_comp, the per-block CRC32 check on s_aux (it depends only on the inflated
+// bytes, so it runs beside the record scan and the facet kernels).  A wave is enqueued without any host round trip:
+// the submitting thread never waits for the GPU, the PCIe copy of chunk k+1 overlaps the kernels of wave k, and after
+// the last chunk has arrived only the last (small) wave, the coverage resolve and the result read-back remain.
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -18,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/ngs_cuda.h"
+#include "cov_n.cuh"
 #include "coverage.cuh"
 #include "crc32.cuh"
 #include "edits.cuh"
@@ -31,13 +35,6 @@ using namespace ngsq;
 namespace {
 
 thread_local std::string g_create_err;
-
-struct DevFlags {
-  ScanErr scan;
-  uint32_t inflate_err;  // bit (1 << kBlk*) per failure kind
-  uint32_t crc_bad;
-  uint64_t n_records;
-};
 
 struct NcclApi {
   void* lib = nullptr;
@@ -81,12 +78,7 @@ struct ngsq_engine {
   ngsq_config cfg{};
   std::string err;
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr;
-  std::vector<cudaEvent_t> copy_events;
-  std::vector<uint32_t> copy_upto;  // h_blocks.size() once the chunk of copy_events[i] was appended
-  uint32_t launched = 0;            // blocks [0, launched) have been handed to the inflate kernels
-  struct InflateEvents { cudaEvent_t begin, decoded_from, decoded, end, crc_begin, crc_end; };
-  std::vector<InflateEvents> inflate_events;
-  cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr, ev_f = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_b = nullptr, ev_d = nullptr, ev_e = nullptr, ev_f = nullptr, ev_g = nullptr;
   bool run_started = false, finished = false;
 
   // references / coverage
@@ -104,46 +96,66 @@ struct ngsq_engine {
   int64_t* d_tile = nullptr;
   uint32_t tile_cap = 0;
 
-  // results
+  // results: [fixed | per-contig coverage slots | quality table, qpos_cap rows]
   uint64_t* d_res = nullptr;
   size_t res_words = 0, res_cap_words = 0;
   uint32_t qual_off = R_FIXED_WORDS;
   uint32_t qpos_cap = 0;
+  uint32_t qpos_dirty = 0;  // quality rows an earlier run may have written (zeroed at the next start)
   std::vector<uint64_t> h_res;
   uint32_t h_qpos = 0;
 
-  // input / inflate
-  struct CompSeg { uint8_t* ptr; size_t cap, used; };
-  std::vector<CompSeg> comp_segs;  // compressed bytes live in segments: descriptors hold absolute addresses
-  uint8_t* d_out = nullptr;
-  size_t out_cap = 0;
-  uint64_t out_used = 0;
-  BlockDesc* d_blocks = nullptr;
-  uint32_t blocks_cap = 0;
-  std::vector<BlockDesc> h_blocks;
-  std::vector<uint64_t> h_coff, h_out_off;
+  // submitted blocks (host tables for the whole run; the device only ever sees one wave)
+  std::vector<BlockDesc> h_blocks;  // in_off absolute, out_off = inflated offset in the whole stream
   std::vector<uint32_t> h_crc;
+  uint64_t out_used = 0;            // inflated bytes submitted so far
   uint64_t comp_bytes_total = 0;
-  uint32_t* d_status = nullptr;
-  uint32_t* d_crcx = nullptr;    // expected CRC32 of every block
-  size_t crcx_cap = 0;
-  uint32_t* d_bitmap = nullptr;  // inflate: one bit per inflated byte ("a match starts here"), kBitmapWords per block
-  size_t bitmap_cap = 0;         // blocks
-  uint32_t* d_queue = nullptr;
-  uint64_t* d_agree = nullptr;  // 3 words exchanged before the reduce
-  uint32_t n_launches = 0;
-  static constexpr uint32_t kQueueSlots = 4096;
-  uint64_t *d_out_off = nullptr, *d_coff = nullptr, *d_base = nullptr, *d_rec = nullptr;
-  uint32_t *d_first = nullptr, *d_landed = nullptr, *d_count = nullptr;
-  uint32_t aux_cap = 0;
+  struct Chunk { cudaEvent_t copied; uint32_t blocks_end; };
+  std::vector<Chunk> chunks;        // host submits: blocks [.., blocks_end) are on the device once `copied` fired
+  uint32_t launched = 0;            // blocks [0, launched) have been handed to a wave
+
+  // compressed staging ring
+  struct CompSeg { uint8_t* ptr; size_t cap, used; uint32_t blocks_end; };
+  std::vector<CompSeg> comp_segs;
+  size_t comp_total = 0;
+
+  // waves
+  struct Wave { cudaEvent_t begin, decoded_from, decoded, resolved, scan_end, facets_end, crc_begin, crc_end; uint32_t b1; bool scanned; };
+  std::vector<Wave> waves;
+  uint32_t headroom = 0;
+  uint8_t* d_slot[2] = {nullptr, nullptr};
+  size_t slot_cap[2] = {0, 0};       // data bytes behind the headroom
+  BlockDesc* d_wblocks[2] = {nullptr, nullptr};
+  uint32_t* d_wcrc[2] = {nullptr, nullptr};
+  uint32_t wtab_cap[2] = {0, 0};
+  uint32_t *d_wstatus = nullptr, *d_first = nullptr, *d_landed = nullptr, *d_count = nullptr;
+  uint64_t* d_base = nullptr;
+  uint32_t scan_cap = 0;
+  uint32_t* d_bitmap = nullptr;
+  size_t bitmap_cap = 0;             // blocks
+  uint64_t* d_rec = nullptr;
   uint64_t rec_cap = 0;
-  DevFlags* d_flags = nullptr;
+  uint32_t* d_mark = nullptr;
+  uint64_t mark_cap = 0;
+  uint32_t* d_queue = nullptr;
+  RunState* d_state = nullptr;
+  RunState* h_state = nullptr;       // pinned
+  uint64_t* h_prog = nullptr;        // pinned ring: {rec_base, wave_rec} after each wave's scan (ngsq_progress)
+  uint32_t prog_seen = 0;            // waves whose probe has been consumed
+  uint64_t prog_records = 0;
+  struct Staging { BlockDesc* blocks = nullptr; uint32_t* crc = nullptr; uint32_t cap = 0; cudaEvent_t done = nullptr; bool busy = false; };
+  Staging staging[3];
   CrcTables* d_crc_tables = nullptr;
 
+  // shard range (virtual offsets -> blocks, resolved as the blocks arrive)
   uint64_t first_voff = 0, end_voff = 0;
-  bool range_set = false;
+  bool range_set = false, start_resolved = false, end_resolved = false;
+  uint32_t start_block = 0, start_uo = 0, end_block = 0, end_uo = 0;
+
   ngsq_stats stats{};
   uint32_t other_launches = 0;
+  size_t facet_smem = 0;
+  int facet_occ = 0;
 
   // Edits facet (NGSQ_F_EDITS): per-contig FASTA codes, per-position counters, result block
   std::vector<EditsContig> ed_contigs;
@@ -153,7 +165,6 @@ struct ngsq_engine {
   uint64_t ed_pos_total = 0;
   unsigned long long* d_ed_res = nullptr;
   std::vector<uint64_t> h_ed_res;
-  cudaEvent_t ev_g = nullptr;
 
   // Genomic Features facet (NGSQ_F_FEATURES): per contig and class, sorted starts / stops; nine counters
   std::vector<FeatureContig> ft_contigs;
@@ -167,9 +178,15 @@ struct ngsq_engine {
   // nccl
   void* comm = nullptr;
   int n_ranks = 1, rank = 0;
+  bool layout_agreed = false;
 };
 
 namespace {
+
+constexpr uint32_t kDefaultHeadroom = 16u << 20;       // longest record that may straddle two waves
+constexpr uint32_t kDefaultQualPositions = 1u << 17;   // rows of the global quality table (98 MB)
+constexpr uint32_t kProgSlots = 1024;
+constexpr size_t kDefaultCompRing = (size_t)8 << 30;   // compressed staging kept on the device when the caller reserves nothing
 
 int fail(ngsq_engine* e, int code, const char* fmt, ...) {
   char buf[512];
@@ -187,68 +204,33 @@ int fail(ngsq_engine* e, int code, const char* fmt, ...) {
     if (_rc != cudaSuccess) return fail(e, NGSQ_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_rc), __FILE__, __LINE__); \
   } while (0)
 
+// (re)allocates a device buffer that holds no live data; the caller has made sure nothing in flight uses it
 template <class T>
-int grow(ngsq_engine* e, T*& ptr, size_t& cap, size_t need, size_t keep, cudaStream_t s, size_t pad = 0) {
-  if (need <= cap) return NGSQ_OK;
-  size_t ncap = std::max(need, cap + cap / 2);
-  T* np = nullptr;
-  cudaError_t rc = cudaMalloc(&np, (ncap + pad) * sizeof(T));
-  if (rc != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc(%zu bytes): %s", (ncap + pad) * sizeof(T), cudaGetErrorString(rc));
-  if (ptr) CU(cudaStreamSynchronize(e->s_aux));  // CRC kernels may still read the old buffer
-  if (ptr && keep) {
-    CU(cudaStreamSynchronize(e->s_comp));
-    CU(cudaMemcpyAsync(np, ptr, keep * sizeof(T), cudaMemcpyDeviceToDevice, s));
-    CU(cudaStreamSynchronize(s));
-  } else if (ptr) {
-    CU(cudaStreamSynchronize(e->s_comp));
-  }
+int fresh(ngsq_engine* e, T*& ptr, size_t n, const char* what) {
   if (ptr) cudaFree(ptr);
-  ptr = np;
-  cap = ncap;
+  ptr = nullptr;
+  cudaError_t rc = cudaMalloc(&ptr, n * sizeof(T));
+  if (rc != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc %s (%zu bytes): %s", what, n * sizeof(T), cudaGetErrorString(rc));
   return NGSQ_OK;
 }
 
-// K2: lane-per-block Huffman decode, then warp-per-block LZ77 resolve (inflate2.cuh)
-int launch_inflate(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_t* out, uint32_t* queue, uint32_t* status,
-                   uint32_t* bitmap, cudaStream_t s, cudaEvent_t ev_decode_from = nullptr, cudaEvent_t ev_decoded = nullptr) {
-  if (!n) return NGSQ_OK;
-  CU(cudaMemsetAsync(bitmap, 0, (size_t)n * kBitmapWords * 4, s));
-  const uint32_t per_cta = kDecThreads;
-  uint32_t grid = std::min<uint32_t>((n + per_cta - 1) / per_cta, (uint32_t)e->n_sm);
-  if (ev_decode_from) CU(cudaEventRecord(ev_decode_from, s));
-  inflate_decode_kernel<<<grid, kDecThreads, kDecSmem, s>>>(out, blocks, n, queue, status, bitmap);
-  CU(cudaGetLastError());
-  if (ev_decoded) CU(cudaEventRecord(ev_decoded, s));
-  // full occupancy (8 CTAs x 8 warps per SM): measured 39 ms / 40 M records vs 47 / 56 / 79 ms with 4 / 3 / 2 CTAs per SM —
-  // latency hiding beats keeping the blocks in flight L2-resident
-  uint32_t rgrid = std::min<uint32_t>((n + kResWarps - 1) / kResWarps, (uint32_t)e->n_sm * 8);
-  inflate_resolve_kernel<<<rgrid, kResThreads, 0, s>>>(out, blocks, n, bitmap, status);
-  CU(cudaGetLastError());
-  return NGSQ_OK;
-}
+uint32_t wave_blocks(const ngsq_engine* e) { return (uint32_t)e->n_sm * kDecThreads; }
 
-// The inflate kernel takes absolute device addresses in BlockDesc.in_off (comp == nullptr).
-int start_run(ngsq_engine* e) {
-  if (e->run_started) return NGSQ_OK;
-  CU(cudaEventRecord(e->ev_start, e->s_comp));
-  if (e->res_words) CU(cudaMemsetAsync(e->d_res, 0, e->res_cap_words * 8, e->s_comp));
-  if ((e->cfg.flags & NGSQ_F_COVERAGE) && e->diff_elems) CU(cudaMemsetAsync(e->d_diff, 0, e->diff_elems * 4, e->s_comp));
-  CU(cudaMemsetAsync(e->d_queue, 0, ngsq_engine::kQueueSlots * 4, e->s_comp));
-  CU(cudaMemsetAsync(e->d_flags, 0, sizeof(DevFlags), e->s_comp));
-  if ((e->cfg.flags & NGSQ_F_FEATURES) && e->d_ft_res) CU(cudaMemsetAsync(e->d_ft_res, 0, F_WORDS * 8, e->s_comp));
-  if ((e->cfg.flags & NGSQ_F_EDITS) && e->d_ed_res) {
-    CU(cudaMemsetAsync(e->d_ed_res, 0, E_WORDS * 8, e->s_comp));
-    if (e->ed_pos_total) {
-      CU(cudaMemsetAsync(e->d_ed_refs, 0, e->ed_pos_total * 4, e->s_comp));
-      CU(cudaMemsetAsync(e->d_ed_alts, 0, e->ed_pos_total * 4, e->s_comp));
-    }
+uint32_t launch_quantum(const ngsq_engine* e) {
+  // One wave = one block per decoder lane: a launch takes about one block-decode latency whatever its size (every
+  // lane decodes its block serially), so smaller launches only add latencies.  When the caller announced the number
+  // of blocks (reserve_blocks), the waves are made equal.
+  if (e->cfg.launch_blocks) return e->cfg.launch_blocks;
+  const uint32_t wave = wave_blocks(e);
+  if (e->cfg.reserve_blocks > wave) {
+    const uint32_t n_waves = (e->cfg.reserve_blocks + wave - 1) / wave;
+    return (e->cfg.reserve_blocks + n_waves - 1) / n_waves;
   }
-  e->run_started = true;
-  return NGSQ_OK;
+  return wave;
 }
 
 int layout_results(ngsq_engine* e, uint32_t qpos) {
-  // fixed | per-contig coverage slots | quality table (last, so its size may differ per run)
+  // fixed | per-contig coverage slots | quality table (last, so that its size may differ per engine)
   uint32_t off = R_FIXED_WORDS;
   e->cov_slot.assign(e->n_ref, 0);
   e->cov_nbins.assign(e->n_ref, 0);
@@ -267,6 +249,7 @@ int layout_results(ngsq_engine* e, uint32_t qpos) {
   return NGSQ_OK;
 }
 
+// Result buffer with room for `qpos` quality rows.  Only between runs (or after ngsq_finish): nothing is in flight.
 int ensure_res(ngsq_engine* e, uint32_t qpos, bool keep) {
   if (qpos < 256) qpos = 256;
   if (qpos <= e->qpos_cap && e->d_res) return NGSQ_OK;
@@ -276,151 +259,409 @@ int ensure_res(ngsq_engine* e, uint32_t qpos, bool keep) {
     uint64_t* np = nullptr;
     size_t ncap = e->res_words;
     cudaError_t rc = cudaMalloc(&np, ncap * 8);
-    if (rc != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc results: %s", cudaGetErrorString(rc));
+    if (rc != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc results (%zu bytes): %s", ncap * 8, cudaGetErrorString(rc));
     CU(cudaMemsetAsync(np, 0, ncap * 8, e->s_comp));
     if (keep && e->d_res && old_words) CU(cudaMemcpyAsync(np, e->d_res, old_words * 8, cudaMemcpyDeviceToDevice, e->s_comp));
     CU(cudaStreamSynchronize(e->s_comp));
     if (e->d_res) cudaFree(e->d_res);
     e->d_res = np;
     e->res_cap_words = ncap;
+    e->layout_agreed = false;  // the layout word carries the table's capacity
   }
   if (e->d_cov_slot) CU(cudaMemcpyAsync(e->d_cov_slot, e->cov_slot.data(), e->n_ref * 4, cudaMemcpyHostToDevice, e->s_comp));
+  CU(cudaStreamSynchronize(e->s_comp));
   return NGSQ_OK;
 }
 
-int append_blocks(ngsq_engine* e, const ngsq_block* blk, uint32_t n, uint64_t dev_base_addr, uint64_t first_coffset,
-                  uint32_t* first_new, uint32_t* n_new) {
-  *first_new = (uint32_t)e->h_blocks.size();
+int start_run(ngsq_engine* e) {
+  if (e->run_started) return NGSQ_OK;
+  if (!e->d_res) { int rc = ensure_res(e, e->cfg.quality_positions ? e->cfg.quality_positions : kDefaultQualPositions, false); if (rc) return rc; }
+  CU(cudaEventRecord(e->ev_start, e->s_comp));
+  // the fixed part, the coverage slots and every quality row an earlier run may have touched
+  const size_t dirty = std::min<size_t>(e->res_words, (size_t)e->qual_off + (size_t)std::max<uint32_t>(e->qpos_dirty, 256) * 94);
+  CU(cudaMemsetAsync(e->d_res, 0, dirty * 8, e->s_comp));
+  if ((e->cfg.flags & NGSQ_F_COVERAGE) && e->diff_elems) CU(cudaMemsetAsync(e->d_diff, 0, e->diff_elems * 4, e->s_comp));
+  memset(e->h_state, 0, sizeof(RunState));
+  e->h_state->bad_block = ~0ull;
+  e->h_state->next_carry = kNoCarry;
+  CU(cudaMemcpyAsync(e->d_state, e->h_state, sizeof(RunState), cudaMemcpyHostToDevice, e->s_comp));
+  if ((e->cfg.flags & NGSQ_F_FEATURES) && e->d_ft_res) CU(cudaMemsetAsync(e->d_ft_res, 0, F_WORDS * 8, e->s_comp));
+  if ((e->cfg.flags & NGSQ_F_EDITS) && e->d_ed_res) {
+    CU(cudaMemsetAsync(e->d_ed_res, 0, E_WORDS * 8, e->s_comp));
+    if (e->ed_pos_total) {
+      CU(cudaMemsetAsync(e->d_ed_refs, 0, e->ed_pos_total * 4, e->s_comp));
+      CU(cudaMemsetAsync(e->d_ed_alts, 0, e->ed_pos_total * 4, e->s_comp));
+    }
+  }
+  // the pinned state block is reused for the read-back at the end: the upload above must have left it
+  CU(cudaStreamSynchronize(e->s_comp));
+  e->run_started = true;
+  return NGSQ_OK;
+}
+
+int append_blocks(ngsq_engine* e, const ngsq_block* blk, uint32_t n, uint64_t dev_base_addr, uint64_t first_coffset) {
   for (uint32_t i = 0; i < n; ++i) {
     const ngsq_block& b = blk[i];
     if (b.csize < b.hdr_len + 8 || b.isize > 65536) return fail(e, NGSQ_E_BAD_BLOCK, "malformed BGZF block at file offset %llu", (unsigned long long)b.coffset);
     if (b.isize == 0) continue;  // empty blocks (incl. the EOF marker) carry nothing
+    if (!e->h_blocks.empty() && b.coffset <= e->h_blocks.back().coff) return fail(e, NGSQ_E_ARG, "chunks must be submitted in file order (block at file offset %llu)", (unsigned long long)b.coffset);
     BlockDesc d;
     d.in_off = dev_base_addr + (b.coffset - first_coffset) + b.hdr_len;
     d.out_off = e->out_used;
     d.clen = b.csize - b.hdr_len - 8;
     d.isize = b.isize;
+    d.coff = b.coffset;
     e->h_blocks.push_back(d);
-    e->h_coff.push_back(b.coffset);
-    e->h_out_off.push_back(e->out_used);
     e->h_crc.push_back(b.crc32);
     e->out_used += b.isize;
   }
-  *n_new = (uint32_t)e->h_blocks.size() - *first_new;
   return NGSQ_OK;
 }
 
-int inflate_new_blocks(ngsq_engine* e, uint32_t first_new, uint32_t n_new) {
-  if (!n_new) return NGSQ_OK;
-  size_t bcap = e->blocks_cap, total = e->h_blocks.size();
-  {
-    size_t cap = bcap;
-    int rc = grow(e, e->d_blocks, cap, total, first_new, e->s_comp);
-    if (rc) return rc;
-    if (cap != bcap) {
-      uint32_t* ns = nullptr;
-      CU(cudaMalloc(&ns, cap * 4));
-      CU(cudaMemsetAsync(ns, 0, cap * 4, e->s_comp));
-      if (e->d_status) {
-        // the verdicts of the blocks decoded so far move along (same stream as the launches that wrote them):
-        // ngsq_finish reports a failed block whichever launch it was in
-        if (first_new) CU(cudaMemcpyAsync(ns, e->d_status, (size_t)first_new * 4, cudaMemcpyDeviceToDevice, e->s_comp));
-        CU(cudaStreamSynchronize(e->s_comp));
-        CU(cudaStreamSynchronize(e->s_aux));
-        cudaFree(e->d_status);
-      }
-      e->d_status = ns;
-    }
-    if (cap > e->crcx_cap) {  // expected CRC32 per block (trailer values), checked right after each launch
-      CU(cudaStreamSynchronize(e->s_comp));
-      CU(cudaStreamSynchronize(e->s_aux));
-      if (e->d_crcx) cudaFree(e->d_crcx);
-      e->d_crcx = nullptr;
-      CU(cudaMalloc(&e->d_crcx, cap * 4));
-      e->crcx_cap = cap;
-    }
-    e->blocks_cap = (uint32_t)cap;
+// first block with file offset >= co among blocks [0, n)
+uint32_t block_lower_bound(const ngsq_engine* e, uint32_t n, uint64_t co) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = lo + (hi - lo) / 2;
+    if (e->h_blocks[mid].coff < co) lo = mid + 1; else hi = mid;
   }
-  {
-    size_t cap = e->out_cap;
-    int rc = grow(e, e->d_out, cap, (size_t)e->out_used, (size_t)e->h_out_off[first_new], e->s_comp, 64);
-    if (rc) return rc;
-    e->out_cap = cap;
+  return lo;
+}
+
+// Resolves the shard's virtual offsets against the blocks submitted so far ([0, n)).  A coffset that names an empty
+// (skipped) block resolves to the start of the next real block.
+int resolve_range(ngsq_engine* e, uint32_t n) {
+  if (!e->start_resolved) {
+    const uint64_t co = e->first_voff >> 16;
+    uint32_t uo = (uint32_t)(e->first_voff & 0xFFFF);
+    const uint32_t b = block_lower_bound(e, n, co);
+    if (b < n) {
+      if (e->h_blocks[b].coff != co) {
+        if (uo) return fail(e, NGSQ_E_ARG, "virtual offset %llu does not address a submitted block", (unsigned long long)e->first_voff);
+      } else if (uo > e->h_blocks[b].isize) return fail(e, NGSQ_E_ARG, "virtual offset %llu: uoffset beyond block", (unsigned long long)e->first_voff);
+      e->start_block = b; e->start_uo = uo; e->start_resolved = true;
+    }
   }
-  CU(cudaMemcpyAsync(e->d_blocks + first_new, e->h_blocks.data() + first_new, n_new * sizeof(BlockDesc), cudaMemcpyHostToDevice, e->s_comp));
-  if (e->n_launches >= ngsq_engine::kQueueSlots) return fail(e, NGSQ_E_ARG, "too many submits in one run (max %u)", ngsq_engine::kQueueSlots);
-  ngsq_engine::InflateEvents ev{};
-  for (cudaEvent_t* x : {&ev.begin, &ev.decoded_from, &ev.decoded, &ev.end, &ev.crc_begin, &ev.crc_end}) CU(cudaEventCreate(x));
-  CU(cudaEventRecord(ev.begin, e->s_comp));
+  if (e->end_voff && !e->end_resolved) {
+    const uint64_t co = e->end_voff >> 16;
+    uint32_t uo = (uint32_t)(e->end_voff & 0xFFFF);
+    const uint32_t b = block_lower_bound(e, n, co);
+    if (b < n) {
+      if (e->h_blocks[b].coff != co) {
+        if (uo) return fail(e, NGSQ_E_ARG, "virtual offset %llu does not address a submitted block", (unsigned long long)e->end_voff);
+      } else if (uo > e->h_blocks[b].isize) return fail(e, NGSQ_E_ARG, "virtual offset %llu: uoffset beyond block", (unsigned long long)e->end_voff);
+      e->end_block = b; e->end_uo = uo; e->end_resolved = true;
+    }
+  }
+  return NGSQ_OK;
+}
+
+// K2: lane-per-block Huffman decode, then warp-per-block LZ77 resolve (inflate2.cuh)
+int launch_inflate(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_t* out, uint32_t* queue, uint32_t* status,
+                   uint32_t* bitmap, cudaStream_t s, cudaEvent_t ev_decode_from = nullptr, cudaEvent_t ev_decoded = nullptr) {
+  if (!n) return NGSQ_OK;
+  CU(cudaMemsetAsync(bitmap, 0, (size_t)n * kBitmapWords * 4, s));
+  CU(cudaMemsetAsync(status, 0, (size_t)n * 4, s));
+  CU(cudaMemsetAsync(queue, 0, 4, s));
+  const uint32_t per_cta = kDecThreads;
+  uint32_t grid = std::min<uint32_t>((n + per_cta - 1) / per_cta, (uint32_t)e->n_sm);
+  if (ev_decode_from) CU(cudaEventRecord(ev_decode_from, s));
+  inflate_decode_kernel<<<grid, kDecThreads, kDecSmem, s>>>(out, blocks, n, queue, status, bitmap);
+  CU(cudaGetLastError());
+  if (ev_decoded) CU(cudaEventRecord(ev_decoded, s));
+  // full occupancy (8 CTAs x 8 warps per SM): measured 39 ms / 40 M records vs 47 / 56 / 79 ms with 4 / 3 / 2 CTAs per SM —
+  // latency hiding beats keeping the blocks in flight L2-resident
+  uint32_t rgrid = std::min<uint32_t>((n + kResWarps - 1) / kResWarps, (uint32_t)e->n_sm * 8);
+  inflate_resolve_kernel<<<rgrid, kResThreads, 0, s>>>(out, blocks, n, bitmap, status);
+  CU(cudaGetLastError());
+  return NGSQ_OK;
+}
+
+// Device buffers of one wave of n blocks / `bytes` inflated bytes in slot `s`.  Growing a buffer waits for the work in
+// flight (only the first waves of a run ever grow anything; reserve_* avoids even that).
+int ensure_wave_buffers(ngsq_engine* e, int s, uint32_t n, uint64_t bytes) {
+  bool synced = false;
+  auto quiesce = [&]() -> int {
+    if (synced) return NGSQ_OK;
+    CU(cudaStreamSynchronize(e->s_comp));
+    CU(cudaStreamSynchronize(e->s_aux));
+    synced = true;
+    return NGSQ_OK;
+  };
   int rc;
-  {
-    if (total > e->bitmap_cap) {
-      // earlier submits' bitmaps are dead once their resolve kernels ran: no need to keep them
-      CU(cudaStreamSynchronize(e->s_comp));
-      if (e->d_bitmap) cudaFree(e->d_bitmap);
-      e->d_bitmap = nullptr;
-      size_t cap = std::max<size_t>(total, e->blocks_cap);
-      cudaError_t r2 = cudaMalloc(&e->d_bitmap, cap * kBitmapWords * 4);
-      if (r2 != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc match bitmap (%zu bytes): %s", cap * kBitmapWords * 4, cudaGetErrorString(r2));
-      e->bitmap_cap = cap;
-    }
-    rc = launch_inflate(e, e->d_blocks + first_new, n_new, e->d_out, e->d_queue + e->n_launches, e->d_status + first_new,
-                        e->d_bitmap + (size_t)first_new * kBitmapWords, e->s_comp, ev.decoded_from, ev.decoded);
-    e->other_launches += 1;  // resolve kernel (the decode kernel is counted as the inflate launch)
+  if (bytes > e->slot_cap[s]) {
+    if ((rc = quiesce())) return rc;
+    // with a reserve hint every slot is sized once for a full wave; otherwise for what the wave needs, with slack
+    size_t want = bytes + bytes / 8;
+    const uint64_t full = (uint64_t)launch_quantum(e) * 65536;
+    if (e->cfg.reserve_inflated) want = (size_t)std::max<uint64_t>(bytes, std::min<uint64_t>(e->cfg.reserve_inflated, full));
+    if ((rc = fresh(e, e->d_slot[s], (size_t)e->headroom + want + 64, "inflated slot"))) return rc;
+    e->slot_cap[s] = want;
   }
+  if (n > e->wtab_cap[s]) {
+    if ((rc = quiesce())) return rc;
+    const uint32_t cap = std::max<uint32_t>(n + n / 8, std::min<uint32_t>(launch_quantum(e), std::max<uint32_t>(e->cfg.reserve_blocks, 64u)));
+    if ((rc = fresh(e, e->d_wblocks[s], cap, "block table"))) return rc;
+    if ((rc = fresh(e, e->d_wcrc[s], cap, "crc table"))) return rc;
+    e->wtab_cap[s] = cap;
+  }
+  if (n > e->scan_cap) {
+    if ((rc = quiesce())) return rc;
+    const uint32_t cap = std::max(e->wtab_cap[0], e->wtab_cap[1]);
+    if ((rc = fresh(e, e->d_wstatus, cap, "status"))) return rc;
+    if ((rc = fresh(e, e->d_first, cap, "scan tables"))) return rc;
+    if ((rc = fresh(e, e->d_landed, cap, "scan tables"))) return rc;
+    if ((rc = fresh(e, e->d_count, (size_t)cap + 1, "scan tables"))) return rc;
+    if ((rc = fresh(e, e->d_base, (size_t)cap + 1, "scan tables"))) return rc;
+    e->scan_cap = cap;
+  }
+  if (n > e->bitmap_cap) {
+    if ((rc = quiesce())) return rc;
+    const size_t cap = std::max<size_t>(n, e->scan_cap);
+    if ((rc = fresh(e, e->d_bitmap, cap * kBitmapWords, "match bitmap"))) return rc;
+    e->bitmap_cap = cap;
+  }
+  const uint64_t need_rec = (e->headroom + std::max<uint64_t>(e->slot_cap[0], e->slot_cap[1])) / 36 + 2;
+  if (need_rec > e->rec_cap) {
+    if ((rc = quiesce())) return rc;
+    if ((rc = fresh(e, e->d_rec, need_rec, "record table"))) return rc;
+    e->rec_cap = need_rec;
+  }
+  if ((e->cfg.flags & NGSQ_F_COVERAGE) && e->cfg.max_records && need_rec > e->mark_cap) {
+    if ((rc = quiesce())) return rc;
+    if ((rc = fresh(e, e->d_mark, need_rec, "record marks"))) return rc;
+    e->mark_cap = need_rec;
+  }
+  return NGSQ_OK;
+}
+
+int new_wave_events(ngsq_engine* e, ngsq_engine::Wave& w) {
+  for (cudaEvent_t* x : {&w.begin, &w.decoded_from, &w.decoded, &w.resolved, &w.scan_end, &w.facets_end, &w.crc_begin, &w.crc_end}) CU(cudaEventCreate(x));
+  return NGSQ_OK;
+}
+
+// One wave: blocks [b0, b1) -> inflate -> CRC (own stream) -> record scan -> facet kernels.  Nothing here waits for the GPU
+// (except when a buffer has to grow).
+int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
+  const uint32_t n = b1 - b0;
+  if (!n) return NGSQ_OK;
+  if (!e->range_set) return fail(e, NGSQ_E_ARG, "ngsq_set_range was not called");
+  int rc = resolve_range(e, b1);
   if (rc) return rc;
-  CU(cudaEventRecord(ev.end, e->s_comp));
-  // CRC32 of the new blocks against their trailers (what noodles-bgzf checks per block), launched per
-  // wave on its own stream: it overlaps the host-to-device copy of the next chunks, the next wave and,
-  // for the last wave, the record scan and the facet kernel
-  CU(cudaStreamWaitEvent(e->s_aux, ev.end, 0));
-  CU(cudaEventRecord(ev.crc_begin, e->s_aux));
+  const uint32_t wi = (uint32_t)e->waves.size();
+  const int s = (int)(wi & 1);
+  cudaStream_t st = e->s_comp;
+  const uint64_t out0 = e->h_blocks[b0].out_off;
+  const uint64_t bytes = e->h_blocks[b1 - 1].out_off + e->h_blocks[b1 - 1].isize - out0;
+  // slot s and its tables were last used by wave wi - 2: its CRC kernel (own stream) must be done with them
+  if (wi >= 2) CU(cudaStreamWaitEvent(st, e->waves[wi - 2].crc_end, 0));
+  if ((rc = ensure_wave_buffers(e, s, n, bytes))) return rc;
+  // pinned staging of the wave's tables (a pageable source would make the "async" copy wait for the stream)
+  ngsq_engine::Staging& sg = e->staging[wi % 3];
+  if (sg.busy) CU(cudaEventSynchronize(sg.done));
+  if (n > sg.cap) {
+    if (sg.blocks) cudaFreeHost(sg.blocks);
+    if (sg.crc) cudaFreeHost(sg.crc);
+    sg.blocks = nullptr; sg.crc = nullptr;
+    const uint32_t cap = std::max<uint32_t>(n, e->wtab_cap[s]);
+    if (cudaHostAlloc((void**)&sg.blocks, (size_t)cap * sizeof(BlockDesc), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void**)&sg.crc, (size_t)cap * 4, cudaHostAllocDefault) != cudaSuccess)
+      return fail(e, NGSQ_E_NOMEM, "cudaHostAlloc wave tables (%u blocks)", cap);
+    sg.cap = cap;
+    if (!sg.done) CU(cudaEventCreateWithFlags(&sg.done, cudaEventDisableTiming));
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    sg.blocks[i] = e->h_blocks[b0 + i];
+    sg.blocks[i].out_off -= out0;
+    sg.crc[i] = e->h_crc[b0 + i];
+  }
+  CU(cudaMemcpyAsync(e->d_wblocks[s], sg.blocks, (size_t)n * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(e->d_wcrc[s], sg.crc, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(sg.done, st));
+  sg.busy = true;
+  // the compressed bytes of the wave: wait for the copy of the last chunk it reads
+  for (const auto& c : e->chunks)
+    if (c.blocks_end >= b1) { CU(cudaStreamWaitEvent(st, c.copied, 0)); break; }
+  ngsq_engine::Wave w{};
+  if ((rc = new_wave_events(e, w))) return rc;
+  w.b1 = b1;
+  uint8_t* slot = e->d_slot[s];
+  uint8_t* out = slot + e->headroom;
+  CU(cudaEventRecord(w.begin, st));
+  rc = launch_inflate(e, e->d_wblocks[s], n, out, e->d_queue, e->d_wstatus, e->d_bitmap, st, w.decoded_from, w.decoded);
+  if (rc) return rc;
+  e->other_launches += 1;  // resolve kernel (the decode kernel is counted as the inflate launch)
+  CU(cudaEventRecord(w.resolved, st));
+  // CRC32 of the wave's blocks against their trailers (what noodles-bgzf checks per block), on its own stream: it
+  // overlaps the record scan and the facet kernels of this wave and the decode of the next one
+  CU(cudaStreamWaitEvent(e->s_aux, w.resolved, 0));
+  CU(cudaEventRecord(w.crc_begin, e->s_aux));
   if (e->cfg.flags & NGSQ_F_VERIFY_CRC) {
-    CU(cudaMemcpyAsync(e->d_crcx + first_new, e->h_crc.data() + first_new, (size_t)n_new * 4, cudaMemcpyHostToDevice, e->s_aux));
-    const uint32_t grid = std::min<uint32_t>((n_new + kCrcThreads / 32 - 1) / (kCrcThreads / 32), (uint32_t)e->n_sm * 6);
-    crc32_kernel<<<grid, kCrcThreads, kCrcSmem, e->s_aux>>>(e->d_out, e->d_blocks + first_new, e->d_crcx + first_new, n_new, e->d_crc_tables,
-                                                            &e->d_flags->crc_bad);
+    const uint32_t grid = std::min<uint32_t>((n + kCrcThreads / 32 - 1) / (kCrcThreads / 32), (uint32_t)e->n_sm * 6);
+    crc32_kernel<<<grid, kCrcThreads, kCrcSmem, e->s_aux>>>(out, e->d_wblocks[s], e->d_wcrc[s], n, e->d_crc_tables, &e->d_state->crc_bad);
     CU(cudaGetLastError());
     e->other_launches++;
   }
-  CU(cudaEventRecord(ev.crc_end, e->s_aux));
-  e->inflate_events.push_back(ev);
-  e->n_launches++;
-  return NGSQ_OK;
-}
+  CU(cudaEventRecord(w.crc_end, e->s_aux));
 
-// Hands blocks [launched, upto) to the inflate kernels.  Launches are sized in whole waves of the
-// decode kernel (one BGZF block per lane, n_sm x kDecThreads lanes): a launch takes the time of its
-// slowest lane, so many small launches would each pay a full block-decode latency.
-int launch_pending(ngsq_engine* e, uint32_t upto) {
-  if (upto <= e->launched) return NGSQ_OK;
-  for (size_t i = 0; i < e->copy_upto.size(); ++i)
-    if (e->copy_upto[i] >= upto) { CU(cudaStreamWaitEvent(e->s_comp, e->copy_events[i], 0)); break; }
-  int rc = inflate_new_blocks(e, e->launched, upto - e->launched);
-  if (rc) return rc;
-  e->launched = upto;
-  return NGSQ_OK;
-}
-
-// waits for the CRC kernels (own stream) and returns the number of blocks whose CRC32 did not match
-int crc_verdict(ngsq_engine* e, uint32_t* n_bad) {
-  CU(cudaStreamSynchronize(e->s_aux));
-  CU(cudaMemcpy(n_bad, &e->d_flags->crc_bad, 4, cudaMemcpyDeviceToHost));
-  return NGSQ_OK;
-}
-
-uint32_t launch_quantum(const ngsq_engine* e) {
-  // One wave: a launch takes about one block-decode latency whatever its size (every lane decodes its
-  // block serially), so smaller launches only add latencies; measured: half waves made e2e 40 % slower.
-  // When the caller announced the number of blocks (reserve_blocks), the waves are made equal so that no
-  // small remainder launch (a full latency for a few blocks) is left for ngsq_finish.
-  if (e->cfg.launch_blocks) return e->cfg.launch_blocks;
-  const uint32_t wave = (uint32_t)e->n_sm * kDecThreads;
-  if (e->cfg.reserve_blocks > wave) {
-    const uint32_t n_waves = (e->cfg.reserve_blocks + wave - 1) / wave;
-    return (e->cfg.reserve_blocks + n_waves - 1) / n_waves;
+  // ---- K3: which part of the wave does the shard own?
+  const bool before_start = !e->start_resolved || e->start_block >= b1;
+  const bool after_end = e->end_resolved && e->end_block < b0;
+  w.scanned = !before_start && !after_end;
+  if (!w.scanned) {
+    status_fold_kernel<<<(n + 255) / 256, 256, 0, st>>>(e->d_wstatus, n, b0, e->d_state);
+    CU(cudaGetLastError());
+    e->other_launches++;
+    CU(cudaEventRecord(w.scan_end, st));
+    CU(cudaEventRecord(w.facets_end, st));
+    e->waves.push_back(w);
+    e->stats.inflate_launches++;
+    return NGSQ_OK;
   }
-  return wave;
+  WaveParams W{};
+  W.d = slot; W.blocks = e->d_wblocks[s]; W.status = e->d_wstatus; W.n_blocks = n; W.first_global = b0; W.headroom = e->headroom;
+  W.first_wave = e->start_block >= b0 ? 1u : 0u;
+  W.final_wave = final_wave ? 1u : 0u;
+  W.n_ref = (int32_t)e->n_ref;
+  W.wave_end = (uint64_t)e->headroom + bytes;
+  W.start_off = W.first_wave ? (uint64_t)e->headroom + (e->h_blocks[e->start_block].out_off - out0) + e->start_uo : 0;
+  W.end_off = ~0ull;
+  if (e->end_resolved && e->end_block < b1) W.end_off = (uint64_t)e->headroom + (e->h_blocks[e->end_block].out_off - out0) + e->end_uo;
+  W.rec_cap = e->rec_cap;
+  W.st = e->d_state; W.first = e->d_first; W.landed = e->d_landed; W.count = e->d_count; W.base = e->d_base; W.rec = e->d_rec;
+  // the previous scanned wave sits in the other slot (waves outside the range carry nothing)
+  const uint8_t* prev = (wi && e->waves[wi - 1].scanned) ? e->d_slot[s ^ 1] : nullptr;
+  CU(cudaMemsetAsync(e->d_landed, 0, (size_t)n * 4, st));
+  wave_begin_kernel<<<1, 1024, 0, st>>>(e->d_state, slot, prev, e->headroom, W.first_wave);
+  find_first_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(W);
+  const uint32_t wg = (n + 1 + 127) / 128;
+  walk_kernel<false, false><<<wg, 128, 0, st>>>(W);
+  check_landed_kernel<false><<<(n + 255) / 256, 256, 0, st>>>(W);
+  chain_fix_kernel<<<1, 1024, 0, st>>>(W);
+  walk_kernel<false, true><<<wg, 128, 0, st>>>(W);
+  check_landed_kernel<true><<<(n + 255) / 256, 256, 0, st>>>(W);
+  scan_counts_kernel<<<1, 1024, 0, st>>>(W);
+  walk_kernel<true, false><<<wg, 128, 0, st>>>(W);
+  CU(cudaGetLastError());
+  e->other_launches += 9;
+  CU(cudaMemcpyAsync(e->h_prog + 2 * (wi % kProgSlots), &e->d_state->rec_base, 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(w.scan_end, st));
+
+  // ---- K4-K8 (+ K11, K12)
+  const bool cov_n = (e->cfg.flags & NGSQ_F_COVERAGE) && e->cfg.max_records;
+  if (e->cfg.flags & (NGSQ_F_RECORD_FACETS | NGSQ_F_COVERAGE)) {
+    FacetParams P{};
+    P.d = slot; P.rec = e->d_rec; P.st = e->d_state; P.st_w = e->d_state; P.blocks = e->d_wblocks[s]; P.headroom = e->headroom;
+    P.cov_scatter = cov_n ? 0u : 1u;
+    P.max_records = e->cfg.max_records; P.gc_seed = e->cfg.gc_seed; P.n_ref = (int32_t)e->n_ref; P.flags = e->cfg.flags;
+    P.ref_len = e->d_ref_len; P.cov_enabled = e->d_cov_enabled; P.diff_base = e->d_diff_base; P.diff = e->d_diff; P.cov_slot = e->d_cov_slot;
+    P.res = e->d_res; P.qual = e->d_res + e->qual_off;
+    P.qpos_smem = kQualSmemPositions;
+    P.qpos_cap = e->qpos_cap;
+    // persistent grid sized for the bound "a record is at least 36 bytes": the record count stays on the device
+    const uint64_t want = (bytes / 36 + 2 + kFacetThreads - 1) / kFacetThreads;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)e->n_sm * e->facet_occ);
+    facets_kernel<<<grid, kFacetThreads, e->facet_smem, st>>>(P);
+    CU(cudaGetLastError());
+    e->other_launches++;
+  }
+  if (cov_n) {
+    CovNParams C{};
+    C.d = slot; C.rec = e->d_rec; C.st = e->d_state; C.max_records = e->cfg.max_records; C.n_ref = (int32_t)e->n_ref;
+    C.ref_len = e->d_ref_len; C.cov_enabled = e->d_cov_enabled; C.diff_base = e->d_diff_base; C.diff = e->d_diff; C.cov_slot = e->d_cov_slot;
+    C.res = e->d_res; C.mark = e->d_mark;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((bytes / 36 + 2 + 255) / 256, (uint64_t)e->n_sm * 8);
+    cov_n_mark_kernel<<<grid, 256, 0, st>>>(C);
+    cov_n_rank_kernel<<<1, 1024, 0, st>>>(C);
+    cov_n_apply_kernel<<<grid, 256, 0, st>>>(C);
+    CU(cudaGetLastError());
+    e->other_launches += 3;
+  }
+  const uint32_t rgrid = (uint32_t)std::min<uint64_t>((bytes / 36 + 2 + 255) / 256, (uint64_t)e->n_sm * 8);
+  if ((e->cfg.flags & NGSQ_F_EDITS) && e->d_ed_res && e->ed_contigs.size() == e->n_ref) {
+    // K11: per-record edit counts and per-position ref / alt counters (the VAF histogram follows in ngsq_finish)
+    EditsParams EP{};
+    EP.d = slot; EP.rec = e->d_rec; EP.st = e->d_state; EP.n_ref = (int32_t)e->n_ref;
+    EP.contigs = e->d_ed_contigs; EP.refs = e->d_ed_refs; EP.alts = e->d_ed_alts; EP.res = e->d_ed_res;
+    edits_kernel<<<rgrid, 256, 0, st>>>(EP);
+    CU(cudaGetLastError());
+    e->other_launches++;
+  }
+  if ((e->cfg.flags & NGSQ_F_FEATURES) && e->d_ft_res && e->ft_model_set && e->ft_contigs.size() == e->n_ref) {
+    // K12: per-record overlap counts against the gene model
+    FeatureParams FP{};
+    FP.d = slot; FP.rec = e->d_rec; FP.st = e->d_state; FP.max_records = e->cfg.max_records; FP.n_ref = (int32_t)e->n_ref;
+    FP.contigs = e->d_ft_contigs; FP.res = e->d_ft_res;
+    memcpy(FP.slot_class, e->ft_slot_class, 8);
+    features_kernel<<<rgrid, 256, 0, st>>>(FP);
+    CU(cudaGetLastError());
+    e->other_launches++;
+  }
+  CU(cudaEventRecord(w.facets_end, st));
+  e->waves.push_back(w);
+  e->stats.inflate_launches++;
+  return NGSQ_OK;
+}
+
+// Hands blocks [launched, upto) to the kernels, one wave per `quantum` blocks.
+int launch_pending(ngsq_engine* e, uint32_t upto, bool final_wave) {
+  const uint32_t quantum = launch_quantum(e);
+  while (e->launched < upto) {
+    const uint32_t b1 = std::min(upto, e->launched + quantum);
+    int rc = launch_wave(e, e->launched, b1, final_wave && b1 == upto);
+    if (rc) return rc;
+    e->launched = b1;
+  }
+  return NGSQ_OK;
+}
+
+// A compressed segment is free again once the wave that reads its last block has been decoded.
+bool seg_retired(ngsq_engine* e, const ngsq_engine::CompSeg& sg, bool wait) {
+  if (!sg.blocks_end) return true;  // holds no blocks
+  if (sg.blocks_end > e->launched) return false;
+  for (const auto& w : e->waves)
+    if (w.b1 >= sg.blocks_end) {
+      if (wait) return cudaEventSynchronize(w.decoded) == cudaSuccess;
+      return cudaEventQuery(w.decoded) == cudaSuccess;
+    }
+  return false;
+}
+
+// Device space for `nbytes` of compressed input: the open segment, a retired one, a new one while the ring may grow;
+// otherwise the caller waits for the oldest wave (back-pressure on the submitting thread).
+int acquire_comp(ngsq_engine* e, size_t nbytes, uint8_t** dst) {
+  const size_t need = (nbytes + 15) & ~size_t(15);
+  if (!e->comp_segs.empty()) {
+    auto& b = e->comp_segs.back();
+    if (b.used + need <= b.cap) { *dst = b.ptr + b.used; b.used += need; return NGSQ_OK; }
+  }
+  auto reuse = [&](size_t i) {
+    ngsq_engine::CompSeg take = e->comp_segs[i];
+    e->comp_segs.erase(e->comp_segs.begin() + i);
+    take.used = need; take.blocks_end = 0;
+    e->comp_segs.push_back(take);
+    *dst = take.ptr;
+  };
+  for (size_t i = 0; i < e->comp_segs.size(); ++i)
+    if (e->comp_segs[i].cap >= need && seg_retired(e, e->comp_segs[i], false)) { reuse(i); return NGSQ_OK; }
+  const size_t limit = e->cfg.comp_ring_bytes ? (size_t)e->cfg.comp_ring_bytes : kDefaultCompRing;
+  // segments of a quarter of the ring (at most 256 MB): one being filled, the others under the decoders
+  const size_t cap = std::max<size_t>(need, std::min<size_t>((size_t)256 << 20, std::max<size_t>(limit / 4, (size_t)1 << 20)));
+  if (!e->comp_segs.empty() && e->comp_total + cap > limit) {
+    // the ring is full: hand every block that is still waiting to a (smaller) wave, then wait for the oldest segment
+    int rc = launch_pending(e, (uint32_t)e->h_blocks.size(), false);
+    if (rc) return rc;
+    for (size_t i = 0; i < e->comp_segs.size(); ++i)
+      if (e->comp_segs[i].cap >= need && seg_retired(e, e->comp_segs[i], true)) { reuse(i); return NGSQ_OK; }
+    // no segment is large enough for this chunk: grow past the limit
+  }
+  uint8_t* p = nullptr;
+  cudaError_t r2 = cudaMalloc(&p, cap + 512);
+  if (r2 != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc compressed segment (%zu bytes): %s", cap, cudaGetErrorString(r2));
+  e->comp_segs.push_back({p, cap, need, 0});
+  e->comp_total += cap;
+  *dst = p;
+  return NGSQ_OK;
 }
 
 }  // namespace
@@ -444,6 +685,7 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   ne->device = device;
   if (cfg) memcpy(&ne->cfg, cfg, std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(ngsq_config), sizeof(ngsq_config)));
   if (!ne->cfg.flags) ne->cfg.flags = NGSQ_F_RECORD_FACETS | NGSQ_F_COVERAGE;
+  ne->headroom = ne->cfg.carry_bytes ? ((ne->cfg.carry_bytes + 63u) & ~63u) : kDefaultHeadroom;
   e = ne;
   auto bail = [&](int code) { std::string m = e->err; ngsq_destroy(e); g_create_err = m; return code; };
 #define CUC(call) do { cudaError_t _r = (call); if (_r != cudaSuccess) { fail(e, NGSQ_E_CUDA, "%s: %s", #call, cudaGetErrorString(_r)); return bail(NGSQ_E_CUDA); } } while (0)
@@ -454,34 +696,32 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   CUC(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
   CUC(cudaStreamCreateWithFlags(&e->s_aux, cudaStreamNonBlocking));
-  for (cudaEvent_t* ev : {&e->ev_start, &e->ev_a, &e->ev_b, &e->ev_c, &e->ev_d, &e->ev_e, &e->ev_f, &e->ev_g}) CUC(cudaEventCreate(ev));
-  CUC(cudaMalloc(&e->d_queue, ngsq_engine::kQueueSlots * 4));
-  CUC(cudaMalloc(&e->d_flags, sizeof(DevFlags)));
+  for (cudaEvent_t* ev : {&e->ev_start, &e->ev_a, &e->ev_b, &e->ev_d, &e->ev_e, &e->ev_f, &e->ev_g}) CUC(cudaEventCreate(ev));
+  CUC(cudaMalloc(&e->d_queue, 64));
+  CUC(cudaMalloc(&e->d_state, sizeof(RunState)));
+  CUC(cudaHostAlloc((void**)&e->h_state, sizeof(RunState), cudaHostAllocDefault));
+  CUC(cudaHostAlloc((void**)&e->h_prog, kProgSlots * 16, cudaHostAllocDefault));
   CUC(cudaMalloc(&e->d_crc_tables, sizeof(CrcTables)));
   // opt-in shared memory sizes are per device: set them for this engine's device (several engines of
   // one process may sit on different GPUs)
   CUC(cudaFuncSetAttribute(crc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCrcSmem));
   CUC(cudaFuncSetAttribute(inflate_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem));
+  e->facet_smem = (size_t)qual_table_bytes(kQualSmemPositions) * (kFacetThreads / 32) + (size_t)(kTlenPad + kGcPad + kCigWords) * 4;
+  CUC(cudaFuncSetAttribute(facets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->facet_smem));
+  CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->facet_occ, facets_kernel, kFacetThreads, e->facet_smem));
+  if (e->facet_occ < 1) e->facet_occ = 1;
   {
     CrcTables t;
     crc_make_tables(t);
     CUC(cudaMemcpy(e->d_crc_tables, &t, sizeof t, cudaMemcpyHostToDevice));
   }
   if (e->cfg.reserve_compressed) {
+    // the caller keeps the whole compressed shard on the device (one segment, no recycling needed)
     uint8_t* p = nullptr;
     size_t cap = e->cfg.reserve_compressed + (e->cfg.reserve_compressed >> 6) + 4096;  // room for 16-byte chunk padding
     CUC(cudaMalloc(&p, cap + 512));
-    e->comp_segs.push_back({p, cap, 0});
-  }
-  if (e->cfg.reserve_inflated) {
-    CUC(cudaMalloc(&e->d_out, e->cfg.reserve_inflated + 64));
-    e->out_cap = e->cfg.reserve_inflated;
-  }
-  if (e->cfg.reserve_blocks) {
-    CUC(cudaMalloc(&e->d_blocks, (size_t)e->cfg.reserve_blocks * sizeof(BlockDesc)));
-    CUC(cudaMalloc(&e->d_status, (size_t)e->cfg.reserve_blocks * 4));
-    CUC(cudaMemset(e->d_status, 0, (size_t)e->cfg.reserve_blocks * 4));
-    e->blocks_cap = e->cfg.reserve_blocks;
+    e->comp_segs.push_back({p, cap, 0, 0});
+    e->comp_total = cap;
   }
 #undef CUC
   *out = e;
@@ -493,13 +733,20 @@ void ngsq_destroy(ngsq_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-  for (auto ev : e->copy_events) cudaEventDestroy(ev);
-  for (auto& p : e->inflate_events) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
-  for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_c, e->ev_d, e->ev_e, e->ev_f, e->ev_g}) if (ev) cudaEventDestroy(ev);
-  void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_res, e->d_out,
-                  e->d_blocks, e->d_status, e->d_crcx, e->d_bitmap, e->d_queue, e->d_agree, e->d_out_off, e->d_coff, e->d_base, e->d_rec, e->d_first, e->d_landed,
-                  e->d_count, e->d_flags, e->d_crc_tables};
+  for (auto& c : e->chunks) cudaEventDestroy(c.copied);
+  for (auto& p : e->waves) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.resolved, p.scan_end, p.facets_end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
+  for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_d, e->ev_e, e->ev_f, e->ev_g}) if (ev) cudaEventDestroy(ev);
+  void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_res, e->d_slot[0], e->d_slot[1],
+                  e->d_wblocks[0], e->d_wblocks[1], e->d_wcrc[0], e->d_wcrc[1], e->d_wstatus, e->d_first, e->d_landed, e->d_count, e->d_base,
+                  e->d_bitmap, e->d_rec, e->d_mark, e->d_queue, e->d_state, e->d_crc_tables};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (e->h_state) cudaFreeHost(e->h_state);
+  if (e->h_prog) cudaFreeHost(e->h_prog);
+  for (auto& sg : e->staging) {
+    if (sg.blocks) cudaFreeHost(sg.blocks);
+    if (sg.crc) cudaFreeHost(sg.crc);
+    if (sg.done) cudaEventDestroy(sg.done);
+  }
   for (void* p : e->ed_allocs) cudaFree(p);
   for (void* p : {(void*)e->d_ed_contigs, (void*)e->d_ed_refs, (void*)e->d_ed_alts, (void*)e->d_ed_res}) if (p) cudaFree(p);
   for (void* p : e->ft_allocs) cudaFree(p);
@@ -517,24 +764,19 @@ int ngsq_reset(ngsq_engine* e) {
   CU(cudaStreamSynchronize(e->s_copy));
   CU(cudaStreamSynchronize(e->s_comp));
   CU(cudaStreamSynchronize(e->s_aux));
-  for (auto ev : e->copy_events) cudaEventDestroy(ev);
-  e->copy_events.clear();
-  e->copy_upto.clear();
+  for (auto& c : e->chunks) cudaEventDestroy(c.copied);
+  e->chunks.clear();
   e->launched = 0;
-  for (auto& p : e->inflate_events) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
-  e->inflate_events.clear();
-  e->h_blocks.clear(); e->h_coff.clear(); e->h_out_off.clear(); e->h_crc.clear();
-  // keep the largest compressed segment, drop the rest
-  if (e->comp_segs.size() > 1) {
-    size_t best = 0;
-    for (size_t i = 1; i < e->comp_segs.size(); ++i) if (e->comp_segs[i].cap > e->comp_segs[best].cap) best = i;
-    for (size_t i = 0; i < e->comp_segs.size(); ++i) if (i != best) cudaFree(e->comp_segs[i].ptr);
-    ngsq_engine::CompSeg keep = e->comp_segs[best];
-    e->comp_segs.assign(1, keep);
-  }
-  for (auto& sg : e->comp_segs) sg.used = 0;
-  e->out_used = 0; e->comp_bytes_total = 0; e->n_launches = 0; e->other_launches = 0;
-  if (e->d_status && e->blocks_cap) CU(cudaMemsetAsync(e->d_status, 0, (size_t)e->blocks_cap * 4, e->s_comp));
+  for (auto& p : e->waves) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.resolved, p.scan_end, p.facets_end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
+  e->waves.clear();
+  e->h_blocks.clear(); e->h_crc.clear();
+  for (auto& sg : e->comp_segs) { sg.used = 0; sg.blocks_end = 0; }
+  for (auto& sg : e->staging) sg.busy = false;
+  e->out_used = 0; e->comp_bytes_total = 0; e->other_launches = 0;
+  e->start_resolved = e->end_resolved = false;
+  e->prog_seen = 0; e->prog_records = 0;
+  // rows of the quality table the next run has to clear; a run that never reached ngsq_finish may have touched any
+  e->qpos_dirty = (e->run_started && !e->finished) ? e->qpos_cap : std::max(e->qpos_dirty, e->h_qpos);
   e->run_started = false; e->finished = false;
   e->h_res.clear(); e->h_qpos = 0;
   e->h_ed_res.clear();
@@ -552,6 +794,7 @@ int ngsq_set_references(ngsq_engine* e, uint32_t n_ref, const uint32_t* ref_len,
   e->cov_enabled.assign(coverage_enabled, coverage_enabled + n_ref);
   if (!(e->cfg.flags & NGSQ_F_COVERAGE)) std::fill(e->cov_enabled.begin(), e->cov_enabled.end(), 0);
   e->diff_base.assign(n_ref, 0);
+  e->layout_agreed = false;
   uint64_t elems = 0;
   uint32_t max_tiles = 1;
   for (uint32_t c = 0; c < n_ref; ++c) {
@@ -580,11 +823,15 @@ int ngsq_set_references(ngsq_engine* e, uint32_t n_ref, const uint32_t* ref_len,
   }
   CU(cudaMalloc(&e->d_tile, (size_t)max_tiles * 8));
   e->tile_cap = max_tiles;
+  // a new header means a new layout: the buffer is rebuilt (and zeroed) with the configured quality capacity
+  const uint32_t qcap = std::max(e->qpos_cap, e->cfg.quality_positions ? e->cfg.quality_positions : kDefaultQualPositions);
   e->qpos_cap = 0;
   e->res_words = 0;
-  int rc = ensure_res(e, 256, false);
+  e->res_cap_words = 0;
+  if (e->d_res) { cudaFree(e->d_res); e->d_res = nullptr; }
+  e->qpos_dirty = 0;
+  int rc = ensure_res(e, qcap, false);
   if (rc) return rc;
-  CU(cudaStreamSynchronize(e->s_comp));
   if (e->cfg.flags & NGSQ_F_EDITS) {
     // sequences loaded for an earlier header are dropped; per-position counters cover 0..=L of every contig
     for (void* p : e->ed_allocs) cudaFree(p);
@@ -698,9 +945,11 @@ int ngsq_set_reference_bases(ngsq_engine* e, uint32_t ref, const uint8_t* letter
 
 int ngsq_set_range(ngsq_engine* e, uint64_t first_rec_voffset, uint64_t end_voffset) {
   if (!e) return NGSQ_E_ARG;
+  if (e->launched) return fail(e, NGSQ_E_ARG, "ngsq_set_range must precede the first submit of a run");
   e->first_voff = first_rec_voffset;
   e->end_voff = end_voffset;
   e->range_set = true;
+  e->start_resolved = e->end_resolved = false;
   return NGSQ_OK;
 }
 
@@ -744,6 +993,7 @@ int ngsq_bgzf_walk(const uint8_t* p, size_t n, uint64_t file_off, ngsq_block* ou
 int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t file_off) {
   if (!e || !bgzf) return fail(e, NGSQ_E_ARG, "bad submit arguments");
   if (e->finished) return fail(e, NGSQ_E_ARG, "submit after finish; call ngsq_reset");
+  if (!e->range_set) return fail(e, NGSQ_E_ARG, "ngsq_set_range must precede the first submit");
   CU(cudaSetDevice(e->device));
   uint32_t n = 0;
   size_t used = 0;
@@ -754,36 +1004,65 @@ int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t fil
   ngsq_bgzf_walk(bgzf, nbytes, file_off, blk.data(), n, &n, &used);
   rc = start_run(e);
   if (rc) return rc;
-  if (e->comp_segs.empty() || e->comp_segs.back().used + nbytes > e->comp_segs.back().cap) {
-    // a segment that is full stays where it is (in-flight descriptors point into it); open a new one
-    size_t cap = std::max<size_t>(nbytes, e->comp_segs.empty() ? nbytes : (size_t)256 << 20);
-    uint8_t* p = nullptr;
-    cudaError_t r2 = cudaMalloc(&p, cap + 512);
-    if (r2 != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc compressed segment (%zu bytes): %s", cap, cudaGetErrorString(r2));
-    e->comp_segs.push_back({p, cap, 0});
-  }
-  ngsq_engine::CompSeg& seg = e->comp_segs.back();
-  uint8_t* dst = seg.ptr + seg.used;
+  uint8_t* dst = nullptr;
+  rc = acquire_comp(e, nbytes, &dst);
+  if (rc) return rc;
   CU(cudaMemcpyAsync(dst, bgzf, nbytes, cudaMemcpyHostToDevice, e->s_copy));
   cudaEvent_t ev;
   CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CU(cudaEventRecord(ev, e->s_copy));
-  e->copy_events.push_back(ev);
-  seg.used += (nbytes + 15) & ~size_t(15);
   e->comp_bytes_total += nbytes;
-  uint32_t first_new, n_new;
-  rc = append_blocks(e, blk.data(), n, (uint64_t)(uintptr_t)dst, file_off, &first_new, &n_new);
-  if (rc) return rc;
-  e->copy_upto.push_back((uint32_t)e->h_blocks.size());
+  rc = append_blocks(e, blk.data(), n, (uint64_t)(uintptr_t)dst, file_off);
+  if (rc) { cudaEventDestroy(ev); return rc; }
+  e->chunks.push_back({ev, (uint32_t)e->h_blocks.size()});
+  e->comp_segs.back().blocks_end = (uint32_t)e->h_blocks.size();
   // inflate in whole waves; the copy of the next chunk overlaps the kernels of this one
-  const uint32_t quantum = launch_quantum(e), pending = (uint32_t)e->h_blocks.size() - e->launched;
-  if (pending >= quantum) return launch_pending(e, e->launched + pending / quantum * quantum);
+  const uint32_t quantum = launch_quantum(e), total = (uint32_t)e->h_blocks.size(), pending = total - e->launched;
+  if (pending >= quantum) return launch_pending(e, e->launched + pending / quantum * quantum, false);
+  // When the caller announced the block count, the last wave is kept small: what is left once the final chunk has
+  // arrived is all that stands between the last copied byte and the results.
+  const uint32_t tail = std::max<uint32_t>(quantum / 8, 1);
+  if (e->cfg.reserve_blocks && !e->cfg.launch_blocks && pending > tail && total < e->cfg.reserve_blocks && e->cfg.reserve_blocks - total <= tail)
+    return launch_pending(e, total, false);
+  return NGSQ_OK;
+}
+
+int ngsq_flush(ngsq_engine* e) {
+  if (!e) return NGSQ_E_ARG;
+  if (e->finished) return NGSQ_OK;
+  CU(cudaSetDevice(e->device));
+  return launch_pending(e, (uint32_t)e->h_blocks.size(), false);
+}
+
+int ngsq_progress(ngsq_engine* e, uint64_t* records) {
+  if (!e || !records) return NGSQ_E_ARG;
+  // waves complete in order: consume the probes of those whose scan has finished (never blocks)
+  while (e->prog_seen < e->waves.size()) {
+    const auto& w = e->waves[e->prog_seen];
+    if (cudaEventQuery(w.scan_end) != cudaSuccess) break;
+    if (w.scanned && e->waves.size() - e->prog_seen <= kProgSlots) {
+      const uint64_t* p = e->h_prog + 2 * (e->prog_seen % kProgSlots);
+      e->prog_records = p[0] + p[1];
+    }
+    e->prog_seen++;
+  }
+  if (e->finished) e->prog_records = e->stats.records;
+  *records = e->prog_records;
+  return NGSQ_OK;
+}
+
+int ngsq_wait_copied(ngsq_engine* e, uint32_t submit_index) {
+  if (!e) return NGSQ_E_ARG;
+  if (submit_index >= e->chunks.size()) return fail(e, NGSQ_E_ARG, "submit %u does not exist in this run (%zu so far)", submit_index, e->chunks.size());
+  CU(cudaSetDevice(e->device));
+  CU(cudaEventSynchronize(e->chunks[submit_index].copied));
   return NGSQ_OK;
 }
 
 int ngsq_submit_device(ngsq_engine* e, const void* dev_bgzf, size_t nbytes, const ngsq_block* blocks, uint32_t n_blocks) {
   if (!e || !dev_bgzf || (!blocks && n_blocks)) return fail(e, NGSQ_E_ARG, "bad submit arguments");
   if (e->finished) return fail(e, NGSQ_E_ARG, "submit after finish; call ngsq_reset");
+  if (!e->range_set) return fail(e, NGSQ_E_ARG, "ngsq_set_range must precede the first submit");
   CU(cudaSetDevice(e->device));
   int rc = start_run(e);
   if (rc) return rc;
@@ -791,30 +1070,10 @@ int ngsq_submit_device(ngsq_engine* e, const void* dev_bgzf, size_t nbytes, cons
   const ngsq_block& last = blocks[n_blocks - 1];
   if (last.coffset + last.csize - blocks[0].coffset > nbytes) return fail(e, NGSQ_E_TRUNCATED, "block table runs past the device buffer");
   e->comp_bytes_total += nbytes;
-  uint32_t first_new, n_new;
-  rc = append_blocks(e, blocks, n_blocks, (uint64_t)(uintptr_t)dev_bgzf, blocks[0].coffset, &first_new, &n_new);
+  rc = append_blocks(e, blocks, n_blocks, (uint64_t)(uintptr_t)dev_bgzf, blocks[0].coffset);
   if (rc) return rc;
-  // resident data: one persistent launch over everything submitted so far (its block queue balances the lanes)
-  return launch_pending(e, (uint32_t)e->h_blocks.size());
-}
-
-static int voff_to_off(ngsq_engine* e, uint64_t voff, uint64_t* off) {
-  uint64_t co = voff >> 16, uo = voff & 0xFFFF;
-  auto it = std::lower_bound(e->h_coff.begin(), e->h_coff.end(), co);
-  if (it == e->h_coff.end()) {  // at or past the last block: only "end of data" is acceptable
-    if (uo == 0) { *off = e->out_used; return NGSQ_OK; }
-    return fail(e, NGSQ_E_ARG, "virtual offset %llu is beyond the submitted data", (unsigned long long)voff);
-  }
-  size_t b = it - e->h_coff.begin();
-  if (*it != co) {
-    // coffset of an empty (skipped) block: resolves to the start of the next real block
-    if (uo != 0) return fail(e, NGSQ_E_ARG, "virtual offset %llu does not address a submitted block", (unsigned long long)voff);
-    *off = e->h_out_off[b];
-    return NGSQ_OK;
-  }
-  if (uo > e->h_blocks[b].isize) return fail(e, NGSQ_E_ARG, "virtual offset %llu: uoffset beyond block", (unsigned long long)voff);
-  *off = e->h_out_off[b] + uo;
-  return NGSQ_OK;
+  // resident data: every wave is enqueued at once (the caller's buffer is used in place)
+  return launch_pending(e, (uint32_t)e->h_blocks.size(), false);
 }
 
 int ngsq_finish(ngsq_engine* e) {
@@ -823,130 +1082,16 @@ int ngsq_finish(ngsq_engine* e) {
   CU(cudaSetDevice(e->device));
   int rc = start_run(e);
   if (rc) return rc;
-  rc = launch_pending(e, (uint32_t)e->h_blocks.size());
-  if (rc) return rc;
-  cudaStream_t s = e->s_comp;
   const uint32_t nb = (uint32_t)e->h_blocks.size();
-  const uint64_t d_end = e->out_used;
-  DevFlags hf{};
-  uint64_t n_rec = 0;
-  uint64_t start_off = 0, end_off = d_end;
-  CU(cudaEventRecord(e->ev_a, s));
-  if (nb) {
-    if (!e->range_set) return fail(e, NGSQ_E_ARG, "ngsq_set_range was not called");
-    rc = voff_to_off(e, e->first_voff, &start_off);
-    if (rc) return rc;
-    if (e->end_voff) { rc = voff_to_off(e, e->end_voff, &end_off); if (rc) return rc; }
-    if (start_off > end_off) return fail(e, NGSQ_E_ARG, "shard range is empty or inverted");
-    // aux tables
-    if (nb + 1 > e->aux_cap) {
-      for (void* p : {(void*)e->d_out_off, (void*)e->d_coff, (void*)e->d_base, (void*)e->d_first, (void*)e->d_landed, (void*)e->d_count}) if (p) cudaFree(p);
-      uint32_t cap = nb + 1 + nb / 4;
-      CU(cudaMalloc(&e->d_out_off, (size_t)cap * 8));
-      CU(cudaMalloc(&e->d_coff, (size_t)cap * 8));
-      CU(cudaMalloc(&e->d_base, (size_t)cap * 8));
-      CU(cudaMalloc(&e->d_first, (size_t)cap * 4));
-      CU(cudaMalloc(&e->d_landed, (size_t)cap * 4));
-      CU(cudaMalloc(&e->d_count, (size_t)cap * 4));
-      e->aux_cap = cap;
-    }
-    e->h_out_off.push_back(d_end);
-    CU(cudaMemcpyAsync(e->d_out_off, e->h_out_off.data(), (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, s));
-    e->h_out_off.pop_back();
-    CU(cudaMemcpyAsync(e->d_coff, e->h_coff.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(e->d_landed, 0, (size_t)nb * 4, s));
-    CU(cudaEventRecord(e->ev_b, s));
-    // K3
-    size_t first_block = std::upper_bound(e->h_out_off.begin(), e->h_out_off.end(), start_off) - e->h_out_off.begin() - 1;
-    find_first_kernel<<<(nb * 32 + 255) / 256, 256, 0, s>>>(e->d_out, e->d_out_off, nb, std::min(d_end, end_off), (int32_t)e->n_ref, start_off, e->d_first);
-    walk_kernel<false><<<(nb + 127) / 128, 128, 0, s>>>(e->d_out, e->d_out_off, nb, d_end, end_off, e->d_first, e->d_landed, e->d_count, nullptr, nullptr, &e->d_flags->scan);
-    check_landed_kernel<<<(nb + 255) / 256, 256, 0, s>>>(e->d_first, e->d_landed, nb, (uint32_t)first_block, &e->d_flags->scan);
-    CU(cudaGetLastError());
-    e->other_launches += 3;
-    CU(cudaMemcpyAsync(&hf, e->d_flags, sizeof hf, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (hf.inflate_err == 0 && hf.scan.chain) {
-      // speculative boundaries failed closure: rebuild them serially (correct by construction)
-      CU(cudaMemsetAsync(&e->d_flags->scan, 0, sizeof(ScanErr), s));
-      CU(cudaMemsetAsync(e->d_landed, 0, (size_t)nb * 4, s));
-      chain_serial_kernel<<<1, 32, 0, s>>>(e->d_out, e->d_out_off, nb, d_end, start_off, end_off, e->d_first, &e->d_flags->scan);
-      walk_kernel<false><<<(nb + 127) / 128, 128, 0, s>>>(e->d_out, e->d_out_off, nb, d_end, end_off, e->d_first, e->d_landed, e->d_count, nullptr, nullptr, &e->d_flags->scan);
-      CU(cudaGetLastError());
-      e->other_launches += 2;
-      CU(cudaMemcpyAsync(&hf, e->d_flags, sizeof hf, cudaMemcpyDeviceToHost, s));
-      CU(cudaStreamSynchronize(s));
-      if (hf.scan.chain) {
-        uint32_t nbad = 0;
-        if (hf.inflate_err == 0 && crc_verdict(e, &nbad) == NGSQ_OK && nbad) { e->finished = true; return fail(e, NGSQ_E_CRC, "%u BGZF block(s) failed the CRC32 check", nbad); }
-        return fail(e, NGSQ_E_CHAIN, "record chain does not close on the shard's end offset");
-      }
-    }
-  } else {
-    CU(cudaEventRecord(e->ev_b, s));
-  }
-  // inflate status
-  if (nb) {
-    std::vector<uint32_t> st;
-    // cheap summary first: any non-zero status?
-    st.resize(nb);
-    CU(cudaMemcpyAsync(st.data(), e->d_status, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    for (uint32_t b = 0; b < nb; ++b)
-      if (st[b]) {
-        e->finished = true;
-        return fail(e, NGSQ_E_BAD_BLOCK, "BGZF block at file offset %llu failed to inflate (%s)", (unsigned long long)e->h_coff[b],
-                    st[b] == kBlkIsize ? "ISIZE mismatch" : st[b] == kBlkOverrun ? "output overrun / bad distance" : "invalid DEFLATE stream");
-      }
-    if (hf.scan.truncated || hf.scan.bad_record) {  // garbage bytes of a block that fails its CRC break the chain too: CRC first
-      uint32_t nbad = 0;
-      rc = crc_verdict(e, &nbad);
-      if (rc) return rc;
-      if (nbad) { e->finished = true; return fail(e, NGSQ_E_CRC, "%u BGZF block(s) failed the CRC32 check", nbad); }
-    }
-    if (hf.scan.truncated) { e->finished = true; return fail(e, NGSQ_E_TRUNCATED, "record chain runs past the end of the submitted data"); }
-    if (hf.scan.bad_record) { e->finished = true; return fail(e, NGSQ_E_BAD_RECORD, "malformed record length on the record chain"); }
-    scan_counts_kernel<<<1, 1024, 0, s>>>(e->d_count, nb, e->d_base, &e->d_flags->n_records);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(&n_rec, &e->d_flags->n_records, 8, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    e->other_launches++;
-    if (n_rec > e->rec_cap) {
-      if (e->d_rec) cudaFree(e->d_rec);
-      e->d_rec = nullptr;
-      uint64_t cap = n_rec + n_rec / 8 + 1024;
-      cudaError_t r2 = cudaMalloc(&e->d_rec, cap * 8);
-      if (r2 != cudaSuccess) return fail(e, NGSQ_E_NOMEM, "cudaMalloc record table (%llu records): %s", (unsigned long long)cap, cudaGetErrorString(r2));
-      e->rec_cap = cap;
-    }
-    if (n_rec) {
-      walk_kernel<true><<<(nb + 127) / 128, 128, 0, s>>>(e->d_out, e->d_out_off, nb, d_end, end_off, e->d_first, nullptr, nullptr, e->d_base, e->d_rec, &e->d_flags->scan);
-      e->other_launches++;
-    }
-  }
-  CU(cudaEventRecord(e->ev_c, s));
-  // K4-K8
-  uint32_t max_lseq = hf.scan.max_lseq;
-  rc = ensure_res(e, max_lseq, true);
+  if (nb && !e->range_set) return fail(e, NGSQ_E_ARG, "ngsq_set_range was not called");
+  rc = launch_pending(e, nb, true);
   if (rc) return rc;
-  if (n_rec) {
-    FacetParams P{};
-    P.d = e->d_out; P.rec = e->d_rec; P.n_rec = n_rec; P.out_off = e->d_out_off; P.coff = e->d_coff; P.d_end = d_end;
-    P.max_records = e->cfg.max_records; P.gc_seed = e->cfg.gc_seed; P.n_ref = (int32_t)e->n_ref; P.flags = e->cfg.flags;
-    P.ref_len = e->d_ref_len; P.cov_enabled = e->d_cov_enabled; P.diff_base = e->d_diff_base; P.diff = e->d_diff; P.cov_slot = e->d_cov_slot;
-    P.res = e->d_res; P.qual = e->d_res + e->qual_off;
-    P.qpos_smem = std::min<uint32_t>(std::max<uint32_t>(max_lseq, 1), 256);
-    P.qpos_cap = e->qpos_cap;
-    size_t smem = (size_t)qual_table_bytes(P.qpos_smem) * (kFacetThreads / 32) + (size_t)(kTlenPad + kGcPad + kCigWords) * 4;
-    CU(cudaFuncSetAttribute(facets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, facets_kernel, kFacetThreads, smem));
-    if (occ < 1) occ = 1;
-    uint64_t want = (n_rec + kFacetThreads - 1) / kFacetThreads;  // a warp takes 32 records per step
-    uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)e->n_sm * occ);
-    facets_kernel<<<grid, kFacetThreads, smem, s>>>(P);
-    CU(cudaGetLastError());
-    e->other_launches++;
+  if (nb) {
+    // a virtual offset behind the last block can only mean "end of data"
+    if (!e->start_resolved && (e->first_voff & 0xFFFF)) return fail(e, NGSQ_E_ARG, "virtual offset %llu is beyond the submitted data", (unsigned long long)e->first_voff);
+    if (e->end_voff && !e->end_resolved && (e->end_voff & 0xFFFF)) return fail(e, NGSQ_E_ARG, "virtual offset %llu is beyond the submitted data", (unsigned long long)e->end_voff);
   }
+  cudaStream_t s = e->s_comp;
   CU(cudaEventRecord(e->ev_d, s));
   // K9
   if (e->cfg.flags & NGSQ_F_COVERAGE) {
@@ -964,78 +1109,81 @@ int ngsq_finish(ngsq_engine* e) {
     CU(cudaGetLastError());
   }
   CU(cudaEventRecord(e->ev_e, s));
-  // K11 (NGSQ_F_EDITS): per-record edit counts and per-position ref / alt counters, then the VAF histogram
+  // K11 teardown (edits.rs:318-334): the VAF histogram over the per-position counters of every wave
   const bool do_edits = (e->cfg.flags & NGSQ_F_EDITS) && e->d_ed_res && e->ed_contigs.size() == e->n_ref;
-  if (do_edits && n_rec) {
-    EditsParams EP{};
-    EP.d = e->d_out; EP.rec = e->d_rec; EP.n_rec = n_rec; EP.out_off = e->d_out_off; EP.n_ref = (int32_t)e->n_ref;
-    EP.contigs = e->d_ed_contigs; EP.refs = e->d_ed_refs; EP.alts = e->d_ed_alts; EP.res = e->d_ed_res;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((n_rec + 255) / 256, (uint64_t)e->n_sm * 8);
-    edits_kernel<<<grid, 256, 0, s>>>(EP);
-    if (e->ed_pos_total) {
-      const uint32_t vgrid = (uint32_t)std::min<uint64_t>((e->ed_pos_total + 255) / 256, (uint64_t)e->n_sm * 8);
-      edits_vaf_kernel<<<vgrid, 256, 0, s>>>(e->d_ed_refs, e->d_ed_alts, e->ed_pos_total, e->d_ed_res);
-    }
+  if (do_edits && e->ed_pos_total && !e->waves.empty()) {
+    const uint32_t vgrid = (uint32_t)std::min<uint64_t>((e->ed_pos_total + 255) / 256, (uint64_t)e->n_sm * 8);
+    edits_vaf_kernel<<<vgrid, 256, 0, s>>>(e->d_ed_refs, e->d_ed_alts, e->ed_pos_total, e->d_ed_res);
     CU(cudaGetLastError());
-    e->other_launches += 2;
+    e->other_launches += 1;
   }
   if (do_edits) {
     e->h_ed_res.resize(E_WORDS);
     CU(cudaMemcpyAsync(e->h_ed_res.data(), e->d_ed_res, E_WORDS * 8, cudaMemcpyDeviceToHost, s));
   }
-  // K12 (NGSQ_F_FEATURES): per-record overlap counts against the gene model
   const bool do_features = (e->cfg.flags & NGSQ_F_FEATURES) && e->d_ft_res && e->ft_model_set && e->ft_contigs.size() == e->n_ref;
   if ((e->cfg.flags & NGSQ_F_FEATURES) && !do_features) return fail(e, NGSQ_E_ARG, "NGSQ_F_FEATURES needs ngsq_set_feature_model before the first submit");
-  if (do_features && n_rec) {
-    FeatureParams FP{};
-    FP.d = e->d_out; FP.rec = e->d_rec; FP.n_rec = n_rec; FP.max_records = e->cfg.max_records; FP.out_off = e->d_out_off; FP.n_ref = (int32_t)e->n_ref;
-    FP.contigs = e->d_ft_contigs; FP.res = e->d_ft_res;
-    memcpy(FP.slot_class, e->ft_slot_class, 8);
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((n_rec + 255) / 256, (uint64_t)e->n_sm * 8);
-    features_kernel<<<grid, 256, 0, s>>>(FP);
-    CU(cudaGetLastError());
-    e->other_launches += 1;
-  }
   if (do_features) {
     e->h_ft_res.resize(F_WORDS);
     CU(cudaMemcpyAsync(e->h_ft_res.data(), e->d_ft_res, F_WORDS * 8, cudaMemcpyDeviceToHost, s));
   }
   CU(cudaEventRecord(e->ev_g, s));
   // the step ends when the CRC stream is done too (its last event closes the device-timed region)
-  if (!e->inflate_events.empty()) CU(cudaStreamWaitEvent(s, e->inflate_events.back().crc_end, 0));
-  e->h_res.resize(e->res_words);
-  CU(cudaMemcpyAsync(e->h_res.data(), e->d_res, e->res_words * 8, cudaMemcpyDeviceToHost, s));
-  uint32_t crc_bad = 0;
-  CU(cudaMemcpyAsync(&crc_bad, &e->d_flags->crc_bad, 4, cudaMemcpyDeviceToHost, s));
+  if (!e->waves.empty()) CU(cudaStreamWaitEvent(s, e->waves.back().crc_end, 0));
+  CU(cudaMemcpyAsync(e->h_state, e->d_state, sizeof(RunState), cudaMemcpyDeviceToHost, s));
+  // results: everything but the quality table now, the table's rows once their number is known
+  e->h_res.assign(e->qual_off, 0);
+  CU(cudaMemcpyAsync(e->h_res.data(), e->d_res, (size_t)e->qual_off * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  const uint32_t qpos = (uint32_t)std::min<uint64_t>(e->h_res[R_QUAL_POSITIONS], e->qpos_cap);
+  e->h_res.resize((size_t)e->qual_off + (size_t)qpos * 94);
+  if (qpos) CU(cudaMemcpyAsync(e->h_res.data() + e->qual_off, e->d_res + e->qual_off, (size_t)qpos * 94 * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaEventRecord(e->ev_f, s));
   CU(cudaStreamSynchronize(s));
   e->finished = true;
-  if (crc_bad) return fail(e, NGSQ_E_CRC, "%u BGZF block(s) failed the CRC32 check", crc_bad);
-  e->h_qpos = (uint32_t)e->h_res[R_QUAL_POSITIONS];
+  e->h_qpos = qpos;
+  e->qpos_dirty = std::max(e->qpos_dirty, std::min<uint32_t>(std::max<uint32_t>(e->h_state->max_lseq, qpos), e->qpos_cap));
   // stats
+  const RunState& R = *e->h_state;
   ngsq_stats& st = e->stats;
-  st.records = n_rec; st.blocks = nb; st.compressed_bytes = e->comp_bytes_total; st.inflated_bytes = d_end; st.max_read_len = max_lseq;
-  st.ms_inflate = 0;
-  st.ms_inflate_decode = 0;
-  st.ms_inflate_resolve = 0;
-  float crc_ms = 0;
-  for (auto& p : e->inflate_events) {
+  st.records = R.rec_base + R.wave_rec; st.blocks = nb; st.compressed_bytes = e->comp_bytes_total; st.inflated_bytes = e->out_used; st.max_read_len = R.max_lseq;
+  st.ms_inflate = st.ms_inflate_decode = st.ms_inflate_resolve = st.ms_crc = st.ms_scan = st.ms_facets = 0;
+  for (auto& p : e->waves) {
     float ms = 0;
-    cudaEventElapsedTime(&ms, p.begin, p.end); st.ms_inflate += ms;
+    cudaEventElapsedTime(&ms, p.begin, p.resolved); st.ms_inflate += ms;
     cudaEventElapsedTime(&ms, p.decoded_from, p.decoded); st.ms_inflate_decode += ms;
-    cudaEventElapsedTime(&ms, p.decoded, p.end); st.ms_inflate_resolve += ms;
-    cudaEventElapsedTime(&ms, p.crc_begin, p.crc_end); crc_ms += ms;
+    cudaEventElapsedTime(&ms, p.decoded, p.resolved); st.ms_inflate_resolve += ms;
+    cudaEventElapsedTime(&ms, p.crc_begin, p.crc_end); st.ms_crc += ms;
+    cudaEventElapsedTime(&ms, p.resolved, p.scan_end); st.ms_scan += ms;
+    cudaEventElapsedTime(&ms, p.scan_end, p.facets_end); st.ms_facets += ms;
   }
-  st.ms_crc = crc_ms;
-  cudaEventElapsedTime(&st.ms_scan, e->ev_b, e->ev_c);
-  cudaEventElapsedTime(&st.ms_facets, e->ev_c, e->ev_d);
   cudaEventElapsedTime(&st.ms_coverage, e->ev_d, e->ev_e);
   cudaEventElapsedTime(&st.ms_edits, e->ev_e, e->ev_g);
   cudaEventElapsedTime(&st.ms_total, e->ev_start, e->ev_f);
-  st.inflate_launches = e->n_launches;
+  if (!e->waves.empty()) cudaEventElapsedTime(&st.ms_tail, e->waves.back().begin, e->ev_f);
+  st.waves = (uint32_t)e->waves.size();
   st.other_launches = e->other_launches;
+  // verdicts, in the order the reference would meet them: a block that does not inflate, a block whose CRC32 is wrong
+  // (its garbage bytes break the record chain too: CRC first), then the record chain, then the records
+  if (R.fatal & kFatalInflate) {
+    const uint64_t b = R.bad_block >> 8;
+    const uint32_t code = (uint32_t)(R.bad_block & 0xFF);
+    return fail(e, NGSQ_E_BAD_BLOCK, "BGZF block at file offset %llu failed to inflate (%s)", (unsigned long long)(b < nb ? e->h_blocks[b].coff : 0),
+                code == kBlkIsize ? "ISIZE mismatch" : code == kBlkOverrun ? "output overrun / bad distance" : "invalid DEFLATE stream");
+  }
+  if (R.crc_bad) return fail(e, NGSQ_E_CRC, "%u BGZF block(s) failed the CRC32 check", R.crc_bad);
+  if ((R.fatal & kFatalTruncated) || (!R.fatal && R.cn_len && !R.end_pending && !R.end_reached))
+    return fail(e, NGSQ_E_TRUNCATED, "record chain runs past the end of the submitted data");
+  if (R.fatal & kFatalBadRecord) return fail(e, NGSQ_E_BAD_RECORD, "malformed record length on the record chain");
+  if (R.fatal & kFatalChain) return fail(e, NGSQ_E_CHAIN, "record chain does not close on the shard's end offset");
+  if (R.fatal & kFatalCarry)
+    return fail(e, NGSQ_E_BAD_RECORD, "a record is longer than the %u bytes the engine carries between two waves (raise ngsq_config.carry_bytes)", e->headroom);
+  if (R.fatal & kFatalRecTable) return fail(e, NGSQ_E_CHAIN, "record table overflow");
   if (e->h_res[R_ERR_QUAL]) return fail(e, NGSQ_E_QUAL_RANGE, "a record holds a quality score above 93 (the reference's decoder rejects it)");
   if (e->h_res[R_ERR_RECORD]) return fail(e, NGSQ_E_BAD_RECORD, "malformed BAM record (field overrun, CIGAR op > 8, reference id out of range, or a mapped pair without reference ids)");
+  if (R.qual_overflow)
+    return fail(e, NGSQ_E_QUAL_CAP, "a read of %u bases exceeds the %u positions of the quality table: call ngsq_set_quality_positions(%u) (or set ngsq_config.quality_positions) and run again",
+                R.qual_overflow, e->qpos_cap, R.qual_overflow);
   if (do_edits && e->h_ed_res[E_ERR]) {
     static const char* const kinds[] = {"", "", "Could not parse read name", "sequence not found in reference FASTA", "record reaches past the end of the reference sequence",
                                         "invalid base in the reference sequence", "step-through: no reference base left", "step-through: no record base left",
@@ -1166,11 +1314,11 @@ int ngsq_comm_init(ngsq_engine* e, int n_ranks, int rank, const char id[128]) {
 
 int ngsq_set_quality_positions(ngsq_engine* e, uint32_t n_positions) {
   if (!e) return NGSQ_E_ARG;
+  if (e->run_started && !e->finished) return fail(e, NGSQ_E_ARG, "ngsq_set_quality_positions: a run is in flight");
   CU(cudaSetDevice(e->device));
-  int rc = ensure_res(e, n_positions, true);
-  if (rc) return rc;
-  CU(cudaStreamSynchronize(e->s_comp));
-  return NGSQ_OK;
+  e->cfg.quality_positions = std::max(e->cfg.quality_positions, n_positions);
+  if (!e->d_cov_slot && !e->n_ref) return NGSQ_OK;  // no layout yet: ngsq_set_references will size the table
+  return ensure_res(e, n_positions, true);
 }
 
 int ngsq_result_buffer(ngsq_engine* e, void** dev_ptr, size_t* n_words) {
@@ -1184,54 +1332,84 @@ int ngsq_result_buffer(ngsq_engine* e, void** dev_ptr, size_t* n_words) {
 int ngsq_refresh_results(ngsq_engine* e) {
   if (!e || !e->finished) return fail(e, NGSQ_E_ARG, "refresh before finish");
   CU(cudaSetDevice(e->device));
-  e->h_res.resize(e->res_words);
-  CU(cudaMemcpyAsync(e->h_res.data(), e->d_res, e->res_words * 8, cudaMemcpyDeviceToHost, e->s_comp));
-  CU(cudaStreamSynchronize(e->s_comp));
+  cudaStream_t s = e->s_comp;
+  e->h_res.assign(e->qual_off, 0);
+  CU(cudaMemcpyAsync(e->h_res.data(), e->d_res, (size_t)e->qual_off * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  const uint32_t qpos = (uint32_t)std::min<uint64_t>(e->h_res[R_QUAL_POSITIONS], e->qpos_cap);
+  e->h_res.resize((size_t)e->qual_off + (size_t)qpos * 94);
+  if (qpos) CU(cudaMemcpyAsync(e->h_res.data() + e->qual_off, e->d_res + e->qual_off, (size_t)qpos * 94 * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  e->h_qpos = qpos;
+  e->qpos_dirty = std::max(e->qpos_dirty, qpos);
   return NGSQ_OK;
 }
 
+// K10.  ONE sum collective in the steady state: every rank parks its own quality length and layout word in its slot of
+// the fixed part (all other ranks hold zeros there), so the all-reduce also hands every rank the max over ranks and the
+// proof that the layouts agree.  Reads longer than kReduceQualRows need a second call for the rest of the table; the very
+// first reduce of an engine agrees on the layout beforehand (a mismatch would mean mismatched counts inside NCCL).
 int ngsq_reduce(ngsq_engine* e, int root) {
   if (!e || !e->finished) return fail(e, NGSQ_E_ARG, "reduce before finish");
   if (!e->comm) return fail(e, NGSQ_E_NCCL, "ngsq_comm_init was not called");
+  if (e->n_ranks > (int)kMaxRanks) return fail(e, NGSQ_E_ARG, "at most %u ranks", kMaxRanks);
   CU(cudaSetDevice(e->device));
   cudaStream_t s = e->s_comp;
   CU(cudaEventRecord(e->ev_a, s));
-  // agree on the quality table size (max over ranks of the longest read with qualities) and check
-  // that every rank packs the same layout: a count mismatch would hang the reduce
-  if (!e->d_agree) CU(cudaMalloc(&e->d_agree, 3 * 8));
   const int ncclUint64 = 5, ncclSum = 0, ncclMax = 2;
-  const uint64_t layout = e->qual_off;
-  uint64_t agree[3] = {e->h_res[R_QUAL_POSITIONS], layout, ~layout};
-  CU(cudaMemcpyAsync(e->d_agree, agree, sizeof agree, cudaMemcpyHostToDevice, s));
-  int rc = g_nccl.AllReduce(e->d_agree, e->d_agree, 3, ncclUint64, ncclMax, e->comm, s);
-  if (rc) return fail(e, NGSQ_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
-  CU(cudaMemcpyAsync(agree, e->d_agree, sizeof agree, cudaMemcpyDeviceToHost, s));
+  auto nccl_err = [&](const char* what, int rc) { return fail(e, NGSQ_E_NCCL, "%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); };
+  const uint64_t layout = (uint64_t)e->qual_off | ((uint64_t)e->qpos_cap << 32);
+  int rc;
+  if (!e->layout_agreed) {
+    uint64_t agree[2] = {layout, ~layout};
+    uint64_t* d_agree = e->d_res + R_RANK_LAYOUT;  // scratch: rewritten below
+    CU(cudaMemcpyAsync(d_agree, agree, sizeof agree, cudaMemcpyHostToDevice, s));
+    rc = g_nccl.AllReduce(d_agree, d_agree, 2, ncclUint64, ncclMax, e->comm, s);
+    if (rc) return nccl_err("ncclAllReduce", rc);
+    CU(cudaMemcpyAsync(agree, d_agree, sizeof agree, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (agree[0] != layout || ~agree[1] != layout)
+      return fail(e, NGSQ_E_ARG, "result layouts differ across ranks: ngsq_set_references must get the same lengths and coverage mask, and ngsq_config.quality_positions the same value, on every rank");
+    e->layout_agreed = true;
+    e->other_launches += 1;
+  }
+  std::vector<uint64_t> slots(2 * kMaxRanks + 0, 0);
+  slots[e->rank] = e->h_qpos;
+  slots[kMaxRanks + e->rank] = layout;
+  CU(cudaMemcpyAsync(e->d_res + R_RANK_QPOS, slots.data(), slots.size() * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(e->d_res + R_QUAL_POSITIONS, 0, 8, s));  // a max, not a sum: rebuilt from the slots
+  const uint32_t rows1 = std::min<uint32_t>(kReduceQualRows, e->qpos_cap);
+  const size_t n1 = (size_t)e->qual_off + (size_t)rows1 * 94;
+  rc = g_nccl.AllReduce(e->d_res, e->d_res, n1, ncclUint64, ncclSum, e->comm, s);
+  if (rc) return nccl_err("ncclAllReduce", rc);
+  CU(cudaMemcpyAsync(slots.data(), e->d_res + R_RANK_QPOS, slots.size() * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  if (agree[1] != layout || ~agree[2] != layout)
-    return fail(e, NGSQ_E_ARG, "result layouts differ across ranks: ngsq_set_references must get the same lengths and coverage mask on every rank");
-  const uint64_t qmax = agree[0];
-  rc = ensure_res(e, (uint32_t)qmax, true);
-  if (rc) return rc;
-  // the max word must not be summed: park it, reduce, restore
-  CU(cudaMemsetAsync(e->d_res + R_QUAL_POSITIONS, 0, 8, s));
-  // the same count on every rank (a rank may hold a larger table from an earlier run)
-  const size_t n_words = (size_t)e->qual_off + (size_t)std::max<uint64_t>(qmax, 256) * 94;
-  rc = g_nccl.Reduce(e->d_res, e->d_res, n_words, ncclUint64, ncclSum, root, e->comm, s);
-  if (rc) return fail(e, NGSQ_E_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  e->other_launches += 1;
+  uint64_t qmax = 0;
+  for (int r = 0; r < e->n_ranks; ++r) {
+    qmax = std::max(qmax, slots[r]);
+    if (slots[kMaxRanks + r] != layout) return fail(e, NGSQ_E_ARG, "result layouts differ across ranks (rank %d)", r);
+  }
+  if (qmax > rows1) {  // long reads: the rest of the table (every rank knows qmax now)
+    const size_t n2 = (size_t)(std::min<uint64_t>(qmax, e->qpos_cap) - rows1) * 94;
+    uint64_t* rest = e->d_res + n1;
+    rc = g_nccl.Reduce(rest, rest, n2, ncclUint64, ncclSum, root, e->comm, s);
+    if (rc) return nccl_err("ncclReduce", rc);
+    e->other_launches += 1;
+  }
   CU(cudaMemcpyAsync(e->d_res + R_QUAL_POSITIONS, &qmax, 8, cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));
-  e->other_launches += 2;
   if ((e->cfg.flags & NGSQ_F_EDITS) && e->d_ed_res && e->h_ed_res.size() == E_WORDS) {
     // additive like everything else: every shard owns whole contigs, so per-position counters never meet
     rc = g_nccl.Reduce(e->d_ed_res, e->d_ed_res, E_WORDS, ncclUint64, ncclSum, root, e->comm, s);
-    if (rc) return fail(e, NGSQ_E_NCCL, "ncclReduce (edits): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    if (rc) return nccl_err("ncclReduce (edits)", rc);
     CU(cudaMemcpyAsync(e->h_ed_res.data(), e->d_ed_res, E_WORDS * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     e->other_launches += 1;
   }
   if ((e->cfg.flags & NGSQ_F_FEATURES) && e->d_ft_res && e->h_ft_res.size() == F_WORDS) {
     rc = g_nccl.Reduce(e->d_ft_res, e->d_ft_res, F_WORDS, ncclUint64, ncclSum, root, e->comm, s);
-    if (rc) return fail(e, NGSQ_E_NCCL, "ncclReduce (features): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    if (rc) return nccl_err("ncclReduce (features)", rc);
     CU(cudaMemcpyAsync(e->h_ft_res.data(), e->d_ft_res, F_WORDS * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     e->other_launches += 1;
@@ -1241,7 +1419,7 @@ int ngsq_reduce(ngsq_engine* e, int root) {
   CU(cudaEventRecord(e->ev_b, s));
   CU(cudaEventSynchronize(e->ev_b));
   cudaEventElapsedTime(&e->stats.ms_reduce, e->ev_a, e->ev_b);
-  e->h_qpos = (uint32_t)qmax;
+  e->stats.other_launches = e->other_launches;
   // touched flags were summed: any non-zero means touched (getters test != 0)
   return NGSQ_OK;
 }
@@ -1255,6 +1433,14 @@ void* ngsq_host_alloc(size_t nbytes) {
 void ngsq_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
+
+int ngsq_host_register(void* p, size_t nbytes) {
+  return cudaHostRegister(p, nbytes, cudaHostRegisterDefault | cudaHostRegisterReadOnly) == cudaSuccess ||
+                 cudaHostRegister(p, nbytes, cudaHostRegisterDefault) == cudaSuccess
+             ? NGSQ_OK : NGSQ_E_CUDA;
+}
+
+int ngsq_host_unregister(void* p) { return cudaHostUnregister(p) == cudaSuccess ? NGSQ_OK : NGSQ_E_CUDA; }
 
 int ngsq_inflate_to_host(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint8_t* out, size_t cap, size_t* n_out) {
   if (!e || !bgzf || !out) return fail(e, NGSQ_E_ARG, "bad arguments");
@@ -1275,7 +1461,7 @@ int ngsq_inflate_to_host(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uin
   for (auto& b : blk) {
     if (b.csize < b.hdr_len + 8 || b.isize > 65536) { cudaFree(d_in); return fail(e, NGSQ_E_BAD_BLOCK, "malformed BGZF block"); }
     if (!b.isize) continue;
-    hb.push_back({(uint64_t)(uintptr_t)d_in + b.coffset + b.hdr_len, total, b.csize - b.hdr_len - 8, b.isize});
+    hb.push_back({(uint64_t)(uintptr_t)d_in + b.coffset + b.hdr_len, total, b.csize - b.hdr_len - 8, b.isize, b.coffset});
     total += b.isize;
   }
   if (n_out) *n_out = (size_t)total;
@@ -1285,9 +1471,8 @@ int ngsq_inflate_to_host(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uin
     cudaStream_t s = e->s_copy;
     CU(cudaMalloc(&d_o, total + 64));
     CU(cudaMalloc(&d_b, hb.size() * sizeof(BlockDesc)));
-    CU(cudaMalloc(&d_st, hb.size() * 4 + 4));
+    CU(cudaMalloc(&d_st, hb.size() * 4 + 64));
     d_q = d_st + hb.size();
-    CU(cudaMemsetAsync(d_st, 0, hb.size() * 4 + 4, s));
     CU(cudaMemcpyAsync(d_in, bgzf, used, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_b, hb.data(), hb.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, s));
     uint32_t* d_bm = nullptr;

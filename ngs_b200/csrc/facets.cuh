@@ -34,7 +34,13 @@ constexpr uint32_t R_ERR_QUAL = 1169;
 constexpr uint32_t R_ERR_RECORD = 1170;
 constexpr uint32_t R_RECORDS = 1171;
 constexpr uint32_t R_QUAL_POSITIONS = 1172;  // max over records with qualities (reduced with max semantics on host)
-constexpr uint32_t R_FIXED_WORDS = 1184;
+// ngsq_reduce: rank r parks its own quality length and layout word here before the all-reduce (every other rank holds 0
+// there), so ONE sum collective also tells every rank the max over ranks and whether the layouts agree
+constexpr uint32_t kMaxRanks = 16;
+constexpr uint32_t R_RANK_QPOS = 1176;                 // [kMaxRanks]
+constexpr uint32_t R_RANK_LAYOUT = R_RANK_QPOS + kMaxRanks;  // [kMaxRanks]
+constexpr uint32_t R_FIXED_WORDS = 1216;
+constexpr uint32_t kReduceQualRows = 1024;  // quality rows that ride in the first collective (longer reads: one more call)
 // per contig slot: [0] touched, [1] pileup_too_large, [2..2051) depth histogram, [2051..) bin sums
 constexpr uint32_t COV_TOUCHED = 0, COV_TOO_LARGE = 1, COV_HIST = 2, COV_BINS = 2051;
 
@@ -42,12 +48,13 @@ constexpr int kFacetThreads = 224;  // 7 warps, each with a private 15 KB qualit
 constexpr uint32_t kTlenPad = 1028, kGcPad = 104, kCigWords = 18 * 32;
 
 struct FacetParams {
-  const uint8_t* d;
-  const uint64_t* rec;
-  uint64_t n_rec;
-  const uint64_t* out_off;
-  const uint64_t* coff;      // file offset of each block (for virtual offsets)
-  uint64_t d_end;
+  const uint8_t* d;          // base of the wave's slot
+  const uint64_t* rec;       // record table of the wave: slot offset | (block + 1) << 40 (recscan.cuh)
+  const RunState* st;        // wave_rec, rec_base, carry_voff, fatal
+  RunState* st_w;            // the same state, for the kernel's own flags (qual_overflow)
+  const BlockDesc* blocks;   // the wave's blocks (file offsets for virtual offsets)
+  uint32_t headroom;
+  uint32_t cov_scatter;      // 1: this kernel scatters coverage (0 with `-n`: cov_n.cuh applies the second pass's counter)
   uint64_t max_records;      // 0 = all
   uint64_t gc_seed;
   int32_t n_ref;
@@ -112,6 +119,9 @@ __device__ __forceinline__ void flush_qual_table(uint32_t* tab_words, uint32_t n
 }
 
 constexpr uint32_t kQualPre = 5;  // quality positions per lane loaded one record ahead (covers reads up to 160 bases)
+// positions privatised in shared memory (per warp: 152 x 100 B; two 7-warp CTAs per SM); the rest goes to the global table.
+// Fixed: the engine streams the file and cannot know the longest read when it launches the first wave.
+constexpr uint32_t kQualSmemPositions = 152;
 
 // loads of one record that phase B needs: quality bytes at positions lane + 32k (0x100 where the
 // string or the shared-memory table ends) and, for lanes < 25 of a GC-eligible record, the three
@@ -156,23 +166,24 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps_per_cta = blockDim.x >> 5;
   const uint64_t n_warps = (uint64_t)gridDim.x * warps_per_cta;
-  const bool do_rec = P.flags & 1u, do_cov = P.flags & 2u;
+  const bool do_rec = P.flags & 1u;
   uint32_t acc = 0;                        // lane k owns counter k (bit k of every record's `bits`)
   uint32_t sum_gc = 0, sum_at = 0, sum_oth = 0;  // warp-uniform
-  uint32_t err_qual = 0, err_rec = 0, max_qpos = 0;
+  uint32_t err_qual = 0, err_rec = 0, max_qpos = 0, qual_over = 0;
+  const uint64_t n_rec = P.st->fatal ? 0 : P.st->wave_rec, rec_base = P.st->rec_base;
+  const bool do_cov = (P.flags & 2u) && P.cov_scatter;
 
-  for (uint64_t r0 = ((uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5)) * 32; r0 < P.n_rec; r0 += n_warps * 32) {
+  for (uint64_t r0 = ((uint64_t)blockIdx.x * warps_per_cta + (threadIdx.x >> 5)) * 32; r0 < n_rec; r0 += n_warps * 32) {
     // ================= phase A: one record per lane =================
     const uint64_t r = r0 + lane;
-    bool valid = r < P.n_rec;
+    bool valid = r < n_rec;
     const uint8_t* p = P.d;
-    uint32_t lseq = 0, f = 0, ncig = 0, lname = 0, mapq = 0, b = 0, uoff = 0;
+    uint32_t lseq = 0, f = 0, ncig = 0, lname = 0, mapq = 0;
+    uint64_t rv = 0;
     int32_t ref = -1, pos = -1, nref = -1, tlen = 0;
     if (valid) {
-      const uint64_t rv = P.rec[r];
-      b = (uint32_t)(rv >> 16);
-      uoff = (uint32_t)(rv & 0xFFFF);
-      p = P.d + P.out_off[b] + uoff;
+      rv = P.rec[r];
+      p = P.d + (rv & kRecOffMask);
       // 36 header bytes at any alignment: ten aligned words, nine funnel shifts
       const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(3));
       const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
@@ -192,7 +203,7 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
     const uint8_t* cig = p + 36 + lname;
     const uint8_t* seq = cig + 4 * (size_t)ncig;
     const uint8_t* qual = seq + (lseq + 1) / 2;
-    const bool in_n = P.max_records == 0 || r < P.max_records;
+    const bool in_n = P.max_records == 0 || rec_base + r < P.max_records;
     const bool rec_on = valid && do_rec && in_n;
 
     // ---- CIGAR: kind tallies (general.rs:103-121) and reference span (utils/cigar.rs:6-11)
@@ -288,7 +299,10 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
         bits |= 1u << 18;
         gc_on = true;
         if (lseq > 100) {
-          const uint64_t voff = (P.coff[b] << 16) | uoff;
+          // the record's BGZF virtual offset: its block's file offset and its offset in that block
+          const uint32_t t = (uint32_t)(rv >> 40);
+          uint64_t voff = P.st->carry_voff;
+          if (t) { const BlockDesc& bd = P.blocks[t - 1]; voff = (bd.coff << 16) | ((rv & kRecOffMask) - P.headroom - bd.out_off); }
           gc_off = (uint32_t)(((splitmix64_dev(P.gc_seed ^ voff) >> 32) * (uint64_t)(lseq - 100)) >> 32);
         }
       }
@@ -359,22 +373,24 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
         }
       }
       bool any_real = q_min < 0xFFu, any_big = q_max > 93;
-      const uint32_t n_s = ls < P.qpos_smem ? ls : P.qpos_smem;
-      for (uint32_t i = 32 * kQualPre + lane; i < n_s; i += 32) {  // shared-memory positions beyond the prefetched ones
-        const uint32_t q = __ldg(ql + i);
-        any_real |= q != 0xFF;
-        if (q > 93) any_big = true;
-        else {
-          uint8_t* c = my_qtab + i * kQualRowBytes + q;
-          *c = (uint8_t)(*c + 1);
+      if (ls > (P.qpos_smem < 32 * kQualPre ? P.qpos_smem : 32 * kQualPre)) {  // warp-uniform: short reads never enter
+        const uint32_t n_s = ls < P.qpos_smem ? ls : P.qpos_smem;
+        for (uint32_t i = 32 * kQualPre + lane; i < n_s; i += 32) {  // shared-memory positions beyond the prefetched ones
+          const uint32_t q = __ldg(ql + i);
+          any_real |= q != 0xFF;
+          if (q > 93) any_big = true;
+          else {
+            uint8_t* c = my_qtab + i * kQualRowBytes + q;
+            *c = (uint8_t)(*c + 1);
+          }
         }
-      }
-      for (uint32_t i = P.qpos_smem + lane; i < ls; i += 32) {  // long reads: the rest goes to the L2-resident global table
-        const uint32_t q = __ldg(ql + i);
-        any_real |= q != 0xFF;
-        if (q > 93) any_big = true;
-        else if (i < P.qpos_cap) atomicAdd((unsigned long long*)&P.qual[(uint64_t)i * 94 + q], 1ull);
-        else err_rec = 1;
+        for (uint32_t i = P.qpos_smem + lane; i < ls; i += 32) {  // long reads: the rest goes to the L2-resident global table
+          const uint32_t q = __ldg(ql + i);
+          any_real |= q != 0xFF;
+          if (q > 93) any_big = true;
+          else if (i < P.qpos_cap) atomicAdd((unsigned long long*)&P.qual[(uint64_t)i * 94 + q], 1ull);
+          else qual_over = ls;  // the global table is too short for this read: the run fails with a request for a longer one
+        }
       }
       any_real = __any_sync(0xFFFFFFFFu, any_real);
       any_big = __any_sync(0xFFFFFFFFu, any_big);
@@ -424,6 +440,7 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
   }
   if (err_qual) P.res[R_ERR_QUAL] = 1;
   if (err_rec) P.res[R_ERR_RECORD] = 1;
+  if (qual_over) atomicMax(&P.st_w->qual_overflow, qual_over);
 }
 
 }  // namespace ngsq

@@ -2,9 +2,9 @@
 // rust-lapper interval lookups built by try_from, 270-355): per record, which kinds of gene-model features its
 // alignment interval overlaps — 5' UTR / 3' UTR / CDS tallies and exonic / intronic / intergenic.
 //
-// STATUS: written against the oracle (oracle/ngsqc_oracle.c, "Genomic Features facet") with its per-record logic
-// shared with a host model (tools/features_model.cpp, tests/test_features_model.py); the CUDA wrapper below has NOT
-// run on a GPU yet.  Nothing launches it unless NGSQ_F_FEATURES is set.
+// Written against the oracle (oracle/ngsqc_oracle.c, "Genomic Features facet"); the per-record logic is shared with a
+// host model (tools/features_model.cpp, tests/test_features_model.py); GPU parity: tests/test_gpu_features.py.  Launched
+// per wave when NGSQ_F_FEATURES is set.
 //
 // No interval tree on the device.  The facet never needs WHICH features overlap a read, only HOW MANY of each name:
 //   * the 5'/3'/CDS chain of features.rs:185-209 hands the k-th overlapping feature of a name to the k-th of the
@@ -18,6 +18,10 @@
 // type; classes 0-2 live in the "exonic translation" set, 3-4 in the "gene regions" set, exactly as try_from files them.
 #pragma once
 #include <stdint.h>
+
+#if defined(__CUDACC__)
+#include "recscan.cuh"
+#endif
 
 #ifndef NGSQ_HD
 #if defined(__CUDACC__)
@@ -112,11 +116,10 @@ NGSQ_HD uint32_t features_record(const uint8_t* rec, int32_t n_ref, const Featur
 #if defined(__CUDACC__)
 
 struct FeatureParams {
-  const uint8_t* d;
-  const uint64_t* rec;
-  uint64_t n_rec;
+  const uint8_t* d;      // base of the wave's slot
+  const uint64_t* rec;   // record table of the wave (recscan.cuh): slot offset in the low 40 bits
+  const RunState* st;    // wave_rec, rec_base, fatal
   uint64_t max_records;  // `-n`: first N records in file order; 0 = all
-  const uint64_t* out_off;
   int32_t n_ref;
   const FeatureContig* contigs;
   uint8_t slot_class[8];
@@ -127,13 +130,13 @@ __global__ void __launch_bounds__(256) features_kernel(FeatureParams P) {
   const uint32_t lane = threadIdx.x & 31;
   uint32_t acc = 0, err = 0;  // lane k owns counter k
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  const uint64_t n_iter = (P.n_rec + stride - 1) / stride;
+  const uint64_t n_rec = P.st->fatal ? 0 : P.st->wave_rec, rec_base = P.st->rec_base;
+  const uint64_t n_iter = (n_rec + stride - 1) / stride;
   for (uint64_t it = 0; it < n_iter; ++it) {  // whole warps stay in the loop: the tallies below are ballots
     const uint64_t r = it * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t bits = 0;
-    if (r < P.n_rec && (P.max_records == 0 || r < P.max_records)) {
-      const uint64_t rv = P.rec[r];
-      const uint32_t st = features_record(P.d + P.out_off[rv >> 16] + (rv & 0xFFFF), P.n_ref, P.contigs, P.slot_class, &bits);
+    if (r < n_rec && (P.max_records == 0 || rec_base + r < P.max_records)) {
+      const uint32_t st = features_record(P.d + (P.rec[r] & kRecOffMask), P.n_ref, P.contigs, P.slot_class, &bits);
       if (st) { err = err > st ? err : st; bits = 0; }
     }
 #pragma unroll

@@ -80,9 +80,10 @@ enum : int { LS_HEADER = 0, LS_DECODE = 1, LS_IDLE = 2 };
 
 struct BlockDesc {
   uint64_t in_off;   // absolute device address of the DEFLATE payload
-  uint64_t out_off;  // offset of this block's first inflated byte
+  uint64_t out_off;  // offset of this block's first inflated byte in its wave (relative to the `out` the kernels get)
   uint32_t clen;     // DEFLATE payload length
   uint32_t isize;    // expected inflated size
+  uint64_t coff;     // file offset of the BGZF block (virtual offsets of its records)
 };
 
 NGSQ_HD uint32_t brev32(uint32_t x) {

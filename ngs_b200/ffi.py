@@ -25,7 +25,7 @@ NGSQ_F_FEATURES = 16
 ERROR_NAMES = {
     0: "NGSQ_OK", -1: "NGSQ_E_ARG", -2: "NGSQ_E_CUDA", -3: "NGSQ_E_TRUNCATED", -4: "NGSQ_E_BAD_BLOCK",
     -5: "NGSQ_E_CRC", -6: "NGSQ_E_BAD_RECORD", -7: "NGSQ_E_QUAL_RANGE", -8: "NGSQ_E_CHAIN",
-    -9: "NGSQ_E_NCCL", -10: "NGSQ_E_NOMEM", -11: "NGSQ_E_EDITS", -12: "NGSQ_E_FEATURES",
+    -9: "NGSQ_E_NCCL", -10: "NGSQ_E_NOMEM", -11: "NGSQ_E_EDITS", -12: "NGSQ_E_FEATURES", -13: "NGSQ_E_QUAL_CAP",
 }
 
 # every symbol include/ngs_cuda.h declares (tests check the library exports all of them)
@@ -36,6 +36,7 @@ EXPORTED = [
     "ngsq_get_stats", "ngsq_nccl_unique_id", "ngsq_comm_init", "ngsq_reduce", "ngsq_set_quality_positions",
     "ngsq_result_buffer", "ngsq_refresh_results", "ngsq_host_alloc", "ngsq_host_free", "ngsq_inflate_to_host",
     "ngsq_set_reference_bases", "ngsq_get_edits", "ngsq_set_feature_model", "ngsq_set_features", "ngsq_get_features",
+    "ngsq_wait_copied", "ngsq_host_register", "ngsq_host_unregister", "ngsq_flush", "ngsq_progress",
 ]
 
 
@@ -49,7 +50,7 @@ class Config(C.Structure):
     _fields_ = [
         ("struct_size", C.c_uint32), ("flags", C.c_uint32), ("gc_seed", C.c_uint64), ("max_records", C.c_uint64),
         ("reserve_compressed", C.c_uint64), ("reserve_inflated", C.c_uint64), ("reserve_blocks", C.c_uint32),
-        ("launch_blocks", C.c_uint32),
+        ("launch_blocks", C.c_uint32), ("quality_positions", C.c_uint32), ("carry_bytes", C.c_uint32), ("comp_ring_bytes", C.c_uint64),
     ]
 
 
@@ -64,7 +65,7 @@ class Stats(C.Structure):
         ("max_read_len", C.c_uint64), ("ms_inflate", C.c_float), ("ms_crc", C.c_float), ("ms_scan", C.c_float),
         ("ms_facets", C.c_float), ("ms_coverage", C.c_float), ("ms_total", C.c_float), ("inflate_launches", C.c_uint32),
         ("other_launches", C.c_uint32), ("ms_inflate_decode", C.c_float), ("ms_inflate_resolve", C.c_float), ("ms_reduce", C.c_float),
-        ("ms_edits", C.c_float),
+        ("ms_edits", C.c_float), ("ms_tail", C.c_float), ("waves", C.c_uint32),
     ]
 
     def as_dict(self):
@@ -124,6 +125,11 @@ def load_library() -> C.CDLL:
     lib.ngsq_set_feature_model.argtypes = [P, u8p, u8p]
     lib.ngsq_set_features.argtypes = [P, C.c_uint32, C.c_uint32, u32p, u32p, u8p]
     lib.ngsq_get_features.argtypes = [P, u64p]
+    lib.ngsq_wait_copied.argtypes = [P, C.c_uint32]
+    lib.ngsq_flush.argtypes = [P]
+    lib.ngsq_progress.argtypes = [P, u64p]
+    lib.ngsq_host_register.argtypes = [P, C.c_size_t]
+    lib.ngsq_host_unregister.argtypes = [P]
     _lib = lib
     return lib
 
@@ -157,10 +163,10 @@ class Engine:
 
     def __init__(self, device: int = 0, flags: int = NGSQ_F_RECORD_FACETS | NGSQ_F_COVERAGE, gc_seed: int = 0,
                  max_records: int = 0, reserve_compressed: int = 0, reserve_inflated: int = 0, reserve_blocks: int = 0,
-                 launch_blocks: int = 0):
+                 launch_blocks: int = 0, quality_positions: int = 0, carry_bytes: int = 0, comp_ring_bytes: int = 0):
         self.lib = load_library()
         cfg = Config(C.sizeof(Config), flags, gc_seed, max_records, reserve_compressed, reserve_inflated, reserve_blocks,
-                     launch_blocks)
+                     launch_blocks, quality_positions, carry_bytes, comp_ring_bytes)
         h = C.c_void_p()
         rc = self.lib.ngsq_create(device, C.byref(cfg), C.byref(h))
         if rc:
@@ -205,6 +211,17 @@ class Engine:
 
     def submit_ptr(self, addr: int, nbytes: int, file_off: int = 0):
         self._check(self.lib.ngsq_submit(self.h, addr, nbytes, file_off))
+
+    def flush(self):
+        self._check(self.lib.ngsq_flush(self.h))
+
+    def progress(self) -> int:
+        v = C.c_uint64(0)
+        self._check(self.lib.ngsq_progress(self.h, C.byref(v)))
+        return v.value
+
+    def wait_copied(self, submit_index: int):
+        self._check(self.lib.ngsq_wait_copied(self.h, submit_index))
 
     def submit_device(self, dev_ptr: int, nbytes: int, blocks, n_blocks: int):
         self._check(self.lib.ngsq_submit_device(self.h, dev_ptr, nbytes, blocks, n_blocks))

@@ -4,14 +4,18 @@
 // app() (305-316 and 350-397) are replaced by one pass of the CUDA engine per GPU.
 //
 //   ngs-cuda-qc qc <BAM> <REFERENCE_GENOME> [-n N] [-o DIR] [-p PREFIX] [--only FACET]
-//               [--cuda-devices 0,1,..] [--cuda-gc-seed S] [--cuda-no-crc] [--cuda-chunk-mb M] [--cuda-perf]
+//               [--cuda-devices 0,1,..] [--cuda-gc-seed S] [--cuda-no-crc] [--cuda-chunk-mb M] [--cuda-buffered-io] [--cuda-perf]
 #include <cstdio>
 #include <cstdlib>
 #include <filesystem>
 #include <iostream>
 #include <optional>
 #include <sstream>
+#include <chrono>
 #include <thread>
+
+#include <fcntl.h>
+#include <unistd.h>
 
 #include "bam.hpp"
 #include "facets.hpp"
@@ -31,37 +35,144 @@ struct QcArgs {
   std::vector<int> devices{0};
   uint64_t gc_seed = 0;
   bool verify_crc = true;
-  size_t chunk_mb = 256;
+  size_t chunk_mb = 64;
+  bool direct_io = true;
   bool perf = false;
 };
 
 void info(const std::string& s) { std::cerr << "INFO " << s << "\n"; }
 
-struct ShardRun {
-  ngsq_engine* engine = nullptr;
-  std::string error;
+// "  [*] Processed 1,000,000 records." (display.rs:43-52: RecordCounter::inc logs every millionth record; Locale::en)
+std::string with_commas(uint64_t v) {
+  std::string d = std::to_string(v), out;
+  for (size_t i = 0; i < d.size(); ++i) {
+    out += d[i];
+    const size_t left = d.size() - 1 - i;
+    if (left && left % 3 == 0) out += ',';
+  }
+  return out;
+}
+
+struct Progress {
+  uint64_t logged = 0;  // millions already reported
+  void report(ngsq_engine* e) {
+    uint64_t n = 0;
+    if (ngsq_progress(e, &n)) return;
+    for (; (logged + 1) * 1000000ull <= n; ++logged) info("  [*] Processed " + with_commas((logged + 1) * 1000000ull) + " records.");
+  }
 };
 
-void run_shard(ngsq_engine* e, const MappedFile& file, const Shard& shard, size_t chunk_bytes, std::string* err) {
+// The shard's bytes, read with O_DIRECT into a ring of page-locked buffers and handed to the engine chunk by chunk:
+// the file read of chunk k+2, the PCIe copy of chunk k+1 and the kernels of chunk k overlap, and the page cache is
+// left alone (the reference reads through a BufReader, bam.rs:41-44).  A chunk ends on a BGZF block boundary; the
+// partial block behind it moves in front of the next read.
+class ChunkReader {
+ public:
+  static constexpr size_t kLead = 1 << 17;  // room in front of every buffer for the previous chunk's partial block
+  ChunkReader(const std::string& path, size_t chunk_bytes, bool direct) : chunk_((chunk_bytes + 4095) & ~size_t(4095)) {
+    fd_ = -1;
+#ifdef O_DIRECT
+    if (direct) fd_ = open(path.c_str(), O_RDONLY | O_DIRECT);
+    direct_ = fd_ >= 0;
+#endif
+    if (fd_ < 0) fd_ = open(path.c_str(), O_RDONLY);
+    if (fd_ < 0) throw std::runtime_error("cannot open " + path);
+    for (auto& b : buf_) {
+      b = (uint8_t*)ngsq_host_alloc(kLead + chunk_ + 4096);
+      if (!b) throw std::runtime_error("cannot allocate pinned staging buffers");
+    }
+  }
+  ~ChunkReader() {
+    for (auto& b : buf_) if (b) ngsq_host_free(b);
+    if (fd_ >= 0) close(fd_);
+  }
+  bool direct() const { return direct_; }
+
+  // streams file bytes [lo, hi) (lo on a block boundary) into e
+  void run(ngsq_engine* e, uint64_t lo, uint64_t hi, Progress* progress) {
+    uint64_t pos = lo & ~uint64_t(4095);  // aligned file position of the next read
+    size_t skip = (size_t)(lo - pos);     // bytes of the first read that precede the shard
+    size_t carry = 0;                     // bytes of a partial block kept from the previous chunk
+    const uint8_t* carry_src = nullptr;
+    uint32_t submits = 0;
+    int32_t used_by[kBufs];
+    for (auto& u : used_by) u = -1;
+    uint64_t file_off = lo;               // file offset of the next byte to submit
+    for (uint32_t k = 0; pos < hi; ++k) {
+      const uint32_t bi = k % kBufs;
+      if (used_by[bi] >= 0) check(e, ngsq_wait_copied(e, (uint32_t)used_by[bi]));  // its last copy must have left the buffer
+      uint8_t* base = buf_[bi] + kLead;
+      size_t want = (size_t)std::min<uint64_t>(chunk_, ((hi + 4095) & ~uint64_t(4095)) - pos);
+      size_t got = 0;
+      while (got < want) {
+        ssize_t r = pread(fd_, base + got, want - got, (off_t)(pos + got));
+        if (r < 0) {
+          if (direct_ && got == 0) {  // a file system that refuses O_DIRECT reads: fall back to buffered reads once
+            int fd2 = open_again_buffered();
+            if (fd2 >= 0) { close(fd_); fd_ = fd2; direct_ = false; continue; }
+          }
+          throw std::runtime_error("read error on the BAM file");
+        }
+        if (r == 0) break;
+        got += (size_t)r;
+      }
+      uint8_t* begin = base + skip;
+      size_t n = got > skip ? got - skip : 0;
+      if (pos + got > hi) n -= (size_t)std::min<uint64_t>(n, pos + got - hi);
+      if (carry) {
+        begin -= carry;
+        memcpy(begin, carry_src, carry);
+        n += carry;
+      }
+      pos += got;
+      skip = 0;
+      const bool last = pos >= hi || got < want;
+      uint32_t nb = 0;
+      size_t used = 0;
+      if (ngsq_bgzf_walk(begin, n, file_off, nullptr, 0, &nb, &used)) throw std::runtime_error("malformed BGZF framing");
+      if (last && used != n) throw std::runtime_error("truncated BGZF block at end of file");
+      if (used) {
+        if (last) check(e, ngsq_flush(e));  // what remains after the last copied byte is one small wave
+        check(e, ngsq_submit(e, begin, used, file_off));
+        used_by[bi] = (int32_t)submits++;
+        file_off += used;
+      }
+      carry = n - used;
+      carry_src = begin + used;
+      if (carry > kLead) throw std::runtime_error("BGZF block larger than 128 KiB");
+      if (progress) progress->report(e);
+      if (got < want) break;
+    }
+  }
+
+ private:
+  int open_again_buffered() {
+    char link[64], path[4096];
+    snprintf(link, sizeof link, "/proc/self/fd/%d", fd_);
+    ssize_t n = readlink(link, path, sizeof path - 1);
+    if (n <= 0) return -1;
+    path[n] = 0;
+    return open(path, O_RDONLY);
+  }
+  static constexpr int kBufs = 3;
+  int fd_ = -1;
+  bool direct_ = false;
+  size_t chunk_;
+  uint8_t* buf_[kBufs] = {nullptr, nullptr, nullptr};
+};
+
+void run_shard(ngsq_engine* e, const std::string& path, const MappedFile& file, const Shard& shard, size_t chunk_bytes, bool direct, bool log_progress,
+               std::string* err) {
   try {
-    if (shard.empty) { check(e, ngsq_finish(e)); return; }
+    if (shard.empty) { check(e, ngsq_set_range(e, 0, 0)); check(e, ngsq_finish(e)); return; }
     uint64_t lo, hi;
     shard_bytes(shard, file.data(), file.size(), &lo, &hi);
     check(e, ngsq_set_range(e, shard.first_voffset, shard.end_voffset));
-    // stream whole-block chunks; K1 framing on the host while the previous chunk inflates
-    uint64_t o = lo;
-    while (o < hi) {
-      uint64_t want = std::min<uint64_t>(chunk_bytes, hi - o);
-      uint32_t nb = 0;
-      size_t used = 0;
-      if (ngsq_bgzf_walk(file.data() + o, want, o, nullptr, 0, &nb, &used)) throw std::runtime_error("malformed BGZF framing");
-      if (used == 0) {  // chunk smaller than one block: take the rest
-        if (ngsq_bgzf_walk(file.data() + o, hi - o, o, nullptr, 0, &nb, &used) || used == 0) throw std::runtime_error("truncated BGZF block at end of file");
-      }
-      check(e, ngsq_submit(e, file.data() + o, used, o));
-      o += used;
-    }
+    Progress progress;
+    ChunkReader reader(path, chunk_bytes, direct);
+    reader.run(e, lo, hi, log_progress ? &progress : nullptr);
     check(e, ngsq_finish(e));
+    if (log_progress) progress.report(e);
   } catch (const std::exception& ex) {
     *err = ex.what();
   }
@@ -95,9 +206,6 @@ int app(const QcArgs& args, const ReferenceGenome& genome, const std::string& ou
   if (edits) flags |= NGSQ_F_EDITS;
   if (args.num_records && edits) throw std::runtime_error("-n with --reference-fasta is not available on the CUDA engine (the second pass shares its record counter, command.rs:384-388)");
   if (args.verify_crc) flags |= NGSQ_F_VERIFY_CRC;
-  if (args.num_records && (flags & NGSQ_F_COVERAGE) && (flags & NGSQ_F_RECORD_FACETS))
-    info("-n applies to the first pass; the second pass (Coverage) is skipped on the CUDA engine when -n is given");
-  if (args.num_records) flags &= ~NGSQ_F_COVERAGE;
   if (args.num_records && n_dev > 1) throw std::runtime_error("-n needs a single device (records are counted in file order)");
 
   std::vector<ngsq_engine*> engines(n_dev, nullptr);
@@ -153,10 +261,12 @@ int app(const QcArgs& args, const ReferenceGenome& genome, const std::string& ou
 
   // the hot path: one thread per GPU
   info("Starting CUDA pass for QC stats.");
+  const auto t_hot = std::chrono::steady_clock::now();
   {
     std::vector<std::thread> ts;
     std::vector<std::string> errs(n_dev);
-    for (uint32_t i = 0; i < n_dev; ++i) ts.emplace_back(run_shard, engines[i], std::cref(file), std::cref(shards[i]), args.chunk_mb << 20, &errs[i]);
+    for (uint32_t i = 0; i < n_dev; ++i)
+      ts.emplace_back(run_shard, engines[i], std::cref(args.src), std::cref(file), std::cref(shards[i]), args.chunk_mb << 20, args.direct_io, i == 0, &errs[i]);
     for (auto& t : ts) t.join();
     for (auto& s : errs) if (!s.empty()) throw std::runtime_error(s);
   }
@@ -167,6 +277,7 @@ int app(const QcArgs& args, const ReferenceGenome& genome, const std::string& ou
     for (auto& t : ts) t.join();
     for (auto& s : errs) if (!s.empty()) throw std::runtime_error("NCCL: " + s);
   }
+  const double hot_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_hot).count();
   ngsq_engine* root = engines[0];
   uint64_t n_records = 0;
   for (auto* e : engines) { ngsq_stats st; ngsq_get_stats(e, &st); n_records += st.records; }
@@ -206,7 +317,7 @@ int app(const QcArgs& args, const ReferenceGenome& genome, const std::string& ou
       pf << (i ? "," : "") << "{\"device\":" << args.devices[i] << ",\"records\":" << st.records << ",\"blocks\":" << st.blocks
          << ",\"compressed_bytes\":" << st.compressed_bytes << ",\"inflated_bytes\":" << st.inflated_bytes << ",\"ms_inflate\":" << st.ms_inflate
          << ",\"ms_crc\":" << st.ms_crc << ",\"ms_scan\":" << st.ms_scan << ",\"ms_facets\":" << st.ms_facets << ",\"ms_coverage\":" << st.ms_coverage
-         << ",\"ms_total\":" << st.ms_total << "}";
+         << ",\"ms_total\":" << st.ms_total << ",\"ms_tail\":" << st.ms_tail << ",\"waves\":" << st.waves << ",\"wall_ms_file_to_results\":" << hot_ms << "}";
     }
     pf << "]\n";
   }
@@ -228,7 +339,7 @@ int qc(const QcArgs& args) {
 
 void usage() {
   std::cerr << "usage: ngs-cuda-qc qc <BAM> <REFERENCE_GENOME> [-n N] [-o DIR] [-p PREFIX] [--only FACET]\n"
-               "                  [--cuda-devices 0,1,..] [--cuda-gc-seed S] [--cuda-no-crc] [--cuda-chunk-mb M] [--cuda-perf]\n";
+               "                  [--cuda-devices 0,1,..] [--cuda-gc-seed S] [--cuda-no-crc] [--cuda-chunk-mb M] [--cuda-buffered-io] [--cuda-perf]\n";
 }
 
 }  // namespace
@@ -259,6 +370,7 @@ extern "C" int ngs_cuda_qc_main(int argc, char** argv) {
       else if (s == "--cuda-no-crc") a.verify_crc = false;
       else if (s == "--cuda-chunk-mb") a.chunk_mb = std::stoull(val());
       else if (s == "--cuda-perf") a.perf = true;
+      else if (s == "--cuda-buffered-io") a.direct_io = false;
       else if (s == "-h" || s == "--help") { usage(); return 0; }
       else if (!s.empty() && s[0] == '-' && s != "-") throw std::runtime_error("unknown flag " + s);
       else pos.push_back(s);

@@ -28,9 +28,9 @@ def test_header_and_library_agree():
 def test_struct_layouts_match_header():
     from ngs_b200 import ffi
     assert C.sizeof(ffi.Block) == 24
-    assert C.sizeof(ffi.Config) == 48
+    assert C.sizeof(ffi.Config) == 64
     assert C.sizeof(ffi.CovInts) == 16 + 2049 * 8
-    assert C.sizeof(ffi.Stats) == 88  # 5 u64, 6 floats, 2 u32, 3 floats (decode / resolve / reduce), padded to 8
+    assert C.sizeof(ffi.Stats) == 96  # 5 u64, 6 floats, 2 u32, 5 floats (decode / resolve / reduce / edits / tail), 1 u32
 
 
 def test_create_fails_loudly_without_gpu():

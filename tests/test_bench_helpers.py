@@ -37,7 +37,8 @@ def test_cpu_sample_takes_whole_contigs_near_the_target(total, monkeypatch):
 
     monkeypatch.setattr(ffi, "synth_bam", fake_synth_bam)
     args = types.SimpleNamespace(cpu_sample=3_000_000)
-    _, _, info, desc = bench.cpu_sample(args, total, 1)
+    wl = bench.workload("wgs", 1, total)
+    _, _, info, desc = bench.cpu_sample(args, wl)
     assert seen["n"] == total and seen["tail"] is False
     chosen = [c for c in range(len(per_contig)) if seen["mask"] >> c & 1]
     big = [c for c in chosen if per_contig[c] > 0.01 * max(per_contig)]  # chromosomes, not chrM
@@ -46,3 +47,35 @@ def test_cpu_sample_takes_whole_contigs_near_the_target(total, monkeypatch):
     assert info["n_records"] <= max(1.5 * args.cpu_sample, min(per_contig[c] for c in big) * 1.01)
     assert info["n_records"] >= 0.5 * args.cpu_sample
     assert str(info["n_records"]) in desc
+
+
+@pytest.mark.parametrize("name,n_ranks", [("wgs", 1), ("wgs", 2), ("wgs", 4), ("wgs", 8), ("c1", 1), ("c4", 1), ("c5", 1)])
+def test_workloads_are_the_named_configs_and_their_shards_cover_every_contig_once(name, n_ranks):
+    import bench
+    wl = bench.workload(name, n_ranks)
+    want_total = {"wgs": 100_000_000 if n_ranks == 1 else 75_000_000 * n_ranks, "c1": 1_000_000, "c4": 2_000_000, "c5": 200_000_000}[name]
+    assert wl["total_records"] == want_total and wl["key"] == f"{name}_n{n_ranks}_{want_total}_l{wl['level']}"
+    masks = [bench.workload_shard(wl, r) for r in range(n_ranks)]
+    assert sum(int(t) for _, t in masks) == 1                      # the unplaced tail has one owner
+    union = 0
+    for m, _ in masks:
+        assert union & m == 0                                      # contig-exclusive
+        union |= m
+    from ngs_b200 import ffi
+    assert union == (1 << len(ffi.synth_layout(wl["shape"], want_total)[0])) - 1
+
+
+def test_committed_fullsize_goldens_load_and_name_their_workload():
+    import glob
+    import bench
+    from helpers import GOLDEN_DIR, load_fullsize_golden
+    files = glob.glob(os.path.join(GOLDEN_DIR, "fullsize_*.npz"))
+    assert files, "no full-size golden committed"
+    for f in files:
+        key = os.path.basename(f)[len("fullsize_"):-4]
+        ints, meta = load_fullsize_golden(key)
+        name, n = meta["key"].split("_")[0], meta["n_ranks"]
+        assert bench.workload(name, n)["key"] == key               # the bench would look this file up
+        assert meta["records"] == meta["total_records"] == sum(meta["shard_records"])
+        if "general" in ints:
+            assert int(ints["general"][0]) == meta["records"]      # General.records.total counts every record once

@@ -93,6 +93,52 @@ def test_num_records(tmp_path):
     assert got["general"] == json.load(open(want_path))["general"]
 
 
+def test_num_records_with_every_default_facet(tmp_path):
+    """`-n` without `--only`: pass 1 stops after n records, pass 2 applies the reference's shared counter
+    (command.rs:350-397) — the whole results file must be the oracle's."""
+    p, bam, bai = _write(tmp_path, 0, 30000)
+    for n in (1234, 20000):
+        _run(["qc", p, "GRCh38_no_alt_AnalysisSet", "-o", str(tmp_path), "-p", f"n{n}", "-n", str(n), "--cuda-gc-seed", "4"])
+        want_path = str(tmp_path / f"o{n}.json")
+        oracle_ints(bam, bai, n_records=n, gc_seed=4, json_path=want_path)
+        assert canonical_results(str(tmp_path / f"n{n}.results.json")) == canonical_results(want_path)
+
+
+def test_progress_lines_and_io_modes(tmp_path):
+    """RecordCounter's log line (display.rs:43-52) every millionth record; O_DIRECT and buffered reads, small and large
+    chunks give the same file."""
+    p, bam, bai = _write(tmp_path, 0, 2_100_000, level=1)
+    r = _run(["qc", p, "GRCh38_no_alt_AnalysisSet", "-o", str(tmp_path), "-p", "a", "--cuda-chunk-mb", "8", "--cuda-perf"])
+    assert "  [*] Processed 1,000,000 records." in r.stderr and "  [*] Processed 2,000,000 records." in r.stderr
+    assert "Processed 2100000 records." in r.stderr
+    _run(["qc", p, "GRCh38_no_alt_AnalysisSet", "-o", str(tmp_path), "-p", "b", "--cuda-chunk-mb", "1", "--cuda-buffered-io"])
+    assert results_digest(str(tmp_path / "a.results.json")) == results_digest(str(tmp_path / "b.results.json"))
+    want_path = str(tmp_path / "o.json")
+    oracle_ints(bam, bai, json_path=want_path)
+    assert canonical_results(str(tmp_path / "a.results.json")) == canonical_results(want_path)
+    perf = json.load(open(tmp_path / "a.perf.json"))
+    assert perf[0]["records"] == 2_100_000 and perf[0]["wall_ms_file_to_results"] > 0 and perf[0]["waves"] >= 1
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+def test_two_devices_shard_one_file_by_bai_ranges(tmp_path):
+    """--cuda-devices 0,1: plan_shards cuts the file at BAI contig extents, one engine per GPU, one NCCL reduce; the
+    results file must be the single-device one (GC window histogram included: offsets are keyed by virtual offsets)."""
+    p, bam, bai = _write(tmp_path, 1, 400000)
+    _run(["qc", p, "GRCh38_no_alt_AnalysisSet", "-o", str(tmp_path), "-p", "two", "--cuda-devices", "0,1", "--cuda-gc-seed", "6"])
+    want_path = str(tmp_path / "o.json")
+    oracle_ints(bam, bai, gc_seed=6, json_path=want_path)
+    assert canonical_results(str(tmp_path / "two.results.json")) == canonical_results(want_path)
+
+
 def test_errors_match_reference_behaviour(tmp_path):
     p, bam, bai = _write(tmp_path, 0, 2000)
     r = _run(["qc", p, "hg19", "-o", str(tmp_path)], check=False)
