@@ -32,6 +32,8 @@ struct CovNParams {
   const uint64_t* diff_base;
   int32_t* diff;
   const uint32_t* cov_slot;
+  const uint32_t* tile_off;
+  int32_t* tile_sum;
   uint64_t* res;
   uint32_t* mark;  // one word per record of the wave
 };
@@ -133,6 +135,8 @@ __global__ void __launch_bounds__(256) cov_n_apply_kernel(CovNParams P) {
       const int64_t e = end < L ? end : L;
       atomicAdd(df + e + 1, -1);
       if (end > L) atomicAdd((unsigned long long*)&P.res[R_NONSENSICAL], (unsigned long long)(end - L));
+      atomicAdd(P.tile_sum + P.tile_off[ref] + (uint32_t)(start >> 12), 1);
+      if (e + 1 <= L) atomicAdd(P.tile_sum + P.tile_off[ref] + (uint32_t)((e + 1) >> 12), -1);
     }
   }
 }

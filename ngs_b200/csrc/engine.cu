@@ -93,8 +93,13 @@ struct ngsq_engine {
   uint32_t* d_cov_slot = nullptr;
   int32_t* d_diff = nullptr;
   uint64_t diff_elems = 0;
-  int64_t* d_tile = nullptr;
+  int64_t* d_tile = nullptr;         // tile bases of the contig being resolved
   uint32_t tile_cap = 0;
+  std::vector<uint32_t> tile_off;    // first tile of every contig in d_tile_sum
+  uint32_t* d_tile_off = nullptr;
+  int32_t* d_tile_sum = nullptr;     // sums of the difference arrays per 4096-position tile, maintained by the scatter
+  uint64_t tile_total = 0;
+  bool cov_bulk = true;              // cov_resolve_kernel<true>: cp.async.bulk staging (NGSQ_COV_BULK=0 selects the direct loads)
 
   // results: [fixed | per-contig coverage slots | quality table, qpos_cap rows]
   uint64_t* d_res = nullptr;
@@ -280,7 +285,10 @@ int start_run(ngsq_engine* e) {
   // the fixed part, the coverage slots and every quality row an earlier run may have touched
   const size_t dirty = std::min<size_t>(e->res_words, (size_t)e->qual_off + (size_t)std::max<uint32_t>(e->qpos_dirty, 256) * 94);
   CU(cudaMemsetAsync(e->d_res, 0, dirty * 8, e->s_comp));
-  if ((e->cfg.flags & NGSQ_F_COVERAGE) && e->diff_elems) CU(cudaMemsetAsync(e->d_diff, 0, e->diff_elems * 4, e->s_comp));
+  if ((e->cfg.flags & NGSQ_F_COVERAGE) && e->diff_elems) {
+    CU(cudaMemsetAsync(e->d_diff, 0, e->diff_elems * 4, e->s_comp));
+    CU(cudaMemsetAsync(e->d_tile_sum, 0, e->tile_total * 4, e->s_comp));
+  }
   memset(e->h_state, 0, sizeof(RunState));
   e->h_state->bad_block = ~0ull;
   e->h_state->next_carry = kNoCarry;
@@ -555,6 +563,7 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
     P.cov_scatter = cov_n ? 0u : 1u;
     P.max_records = e->cfg.max_records; P.gc_seed = e->cfg.gc_seed; P.n_ref = (int32_t)e->n_ref; P.flags = e->cfg.flags;
     P.ref_len = e->d_ref_len; P.cov_enabled = e->d_cov_enabled; P.diff_base = e->d_diff_base; P.diff = e->d_diff; P.cov_slot = e->d_cov_slot;
+    P.tile_off = e->d_tile_off; P.tile_sum = e->d_tile_sum;
     P.res = e->d_res; P.qual = e->d_res + e->qual_off;
     P.qpos_smem = kQualSmemPositions;
     P.qpos_cap = e->qpos_cap;
@@ -569,6 +578,7 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
     CovNParams C{};
     C.d = slot; C.rec = e->d_rec; C.st = e->d_state; C.max_records = e->cfg.max_records; C.n_ref = (int32_t)e->n_ref;
     C.ref_len = e->d_ref_len; C.cov_enabled = e->d_cov_enabled; C.diff_base = e->d_diff_base; C.diff = e->d_diff; C.cov_slot = e->d_cov_slot;
+    C.tile_off = e->d_tile_off; C.tile_sum = e->d_tile_sum;
     C.res = e->d_res; C.mark = e->d_mark;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((bytes / 36 + 2 + 255) / 256, (uint64_t)e->n_sm * 8);
     cov_n_mark_kernel<<<grid, 256, 0, st>>>(C);
@@ -685,6 +695,7 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   ne->device = device;
   if (cfg) memcpy(&ne->cfg, cfg, std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(ngsq_config), sizeof(ngsq_config)));
   if (!ne->cfg.flags) ne->cfg.flags = NGSQ_F_RECORD_FACETS | NGSQ_F_COVERAGE;
+  if (const char* v = getenv("NGSQ_COV_BULK")) ne->cov_bulk = atoi(v) != 0;  // A/B switch for profiles/ (default: the measured winner)
   ne->headroom = ne->cfg.carry_bytes ? ((ne->cfg.carry_bytes + 63u) & ~63u) : kDefaultHeadroom;
   e = ne;
   auto bail = [&](int code) { std::string m = e->err; ngsq_destroy(e); g_create_err = m; return code; };
@@ -711,9 +722,8 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->facet_occ, facets_kernel, kFacetThreads, e->facet_smem));
   if (e->facet_occ < 1) e->facet_occ = 1;
   {
-    CrcTables t;
-    crc_make_tables(t);
-    CUC(cudaMemcpy(e->d_crc_tables, &t, sizeof t, cudaMemcpyHostToDevice));
+    static const CrcTables* const host_tables = [] { CrcTables* t = new CrcTables; crc_make_tables(*t); return t; }();  // 257 KB, built once per process
+    CUC(cudaMemcpy(e->d_crc_tables, host_tables, sizeof(CrcTables), cudaMemcpyHostToDevice));
   }
   if (e->cfg.reserve_compressed) {
     // the caller keeps the whole compressed shard on the device (one segment, no recycling needed)
@@ -736,7 +746,7 @@ void ngsq_destroy(ngsq_engine* e) {
   for (auto& c : e->chunks) cudaEventDestroy(c.copied);
   for (auto& p : e->waves) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.resolved, p.scan_end, p.facets_end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
   for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_d, e->ev_e, e->ev_f, e->ev_g}) if (ev) cudaEventDestroy(ev);
-  void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_res, e->d_slot[0], e->d_slot[1],
+  void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_tile_off, e->d_tile_sum, e->d_res, e->d_slot[0], e->d_slot[1],
                   e->d_wblocks[0], e->d_wblocks[1], e->d_wcrc[0], e->d_wcrc[1], e->d_wstatus, e->d_first, e->d_landed, e->d_count, e->d_base,
                   e->d_bitmap, e->d_rec, e->d_mark, e->d_queue, e->d_state, e->d_crc_tables};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -794,24 +804,33 @@ int ngsq_set_references(ngsq_engine* e, uint32_t n_ref, const uint32_t* ref_len,
   e->cov_enabled.assign(coverage_enabled, coverage_enabled + n_ref);
   if (!(e->cfg.flags & NGSQ_F_COVERAGE)) std::fill(e->cov_enabled.begin(), e->cov_enabled.end(), 0);
   e->diff_base.assign(n_ref, 0);
+  e->tile_off.assign(n_ref, 0);
   e->layout_agreed = false;
-  uint64_t elems = 0;
+  uint64_t elems = 0, tiles = 0;
   uint32_t max_tiles = 1;
   for (uint32_t c = 0; c < n_ref; ++c) {
     e->diff_base[c] = elems;
+    e->tile_off[c] = (uint32_t)tiles;
     if (e->cov_enabled[c]) {
       elems += ((uint64_t)ref_len[c] + 2 + 3) & ~3ull;  // keep every contig 16-byte aligned
-      max_tiles = std::max<uint32_t>(max_tiles, (uint32_t)(((uint64_t)ref_len[c] + 1 + kCovTile - 1) / kCovTile));
+      const uint32_t nt = (uint32_t)(((uint64_t)ref_len[c] + 1 + kCovTile - 1) / kCovTile);
+      max_tiles = std::max<uint32_t>(max_tiles, nt);
+      tiles += nt;
     }
   }
-  for (void* p : {(void*)e->d_ref_len, (void*)e->d_cov_enabled, (void*)e->d_diff_base, (void*)e->d_cov_slot, (void*)e->d_diff, (void*)e->d_tile}) if (p) cudaFree(p);
+  e->tile_total = tiles ? tiles : 1;
+  for (void* p : {(void*)e->d_ref_len, (void*)e->d_cov_enabled, (void*)e->d_diff_base, (void*)e->d_cov_slot, (void*)e->d_diff, (void*)e->d_tile, (void*)e->d_tile_off, (void*)e->d_tile_sum}) if (p) cudaFree(p);
   e->d_ref_len = nullptr; e->d_cov_enabled = nullptr; e->d_diff_base = nullptr; e->d_cov_slot = nullptr; e->d_diff = nullptr; e->d_tile = nullptr;
+  e->d_tile_off = nullptr; e->d_tile_sum = nullptr;
   size_t nr = n_ref ? n_ref : 1;
   CU(cudaMalloc(&e->d_ref_len, nr * 4));
   CU(cudaMalloc(&e->d_cov_enabled, nr));
   CU(cudaMalloc(&e->d_diff_base, nr * 8));
   CU(cudaMalloc(&e->d_cov_slot, nr * 4));
+  CU(cudaMalloc(&e->d_tile_off, nr * 4));
+  CU(cudaMalloc(&e->d_tile_sum, e->tile_total * 4));
   if (n_ref) {
+    CU(cudaMemcpy(e->d_tile_off, e->tile_off.data(), n_ref * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(e->d_ref_len, e->ref_len.data(), n_ref * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(e->d_cov_enabled, e->cov_enabled.data(), n_ref, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(e->d_diff_base, e->diff_base.data(), n_ref * 8, cudaMemcpyHostToDevice));
@@ -1018,6 +1037,9 @@ int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t fil
   e->comp_segs.back().blocks_end = (uint32_t)e->h_blocks.size();
   // inflate in whole waves; the copy of the next chunk overlaps the kernels of this one
   const uint32_t quantum = launch_quantum(e), total = (uint32_t)e->h_blocks.size(), pending = total - e->launched;
+  // The GPU work of a shard takes about as long as its PCIe copy, so it must start early: the FIRST wave is a quarter of
+  // the others (the lanes it leaves idle for one round cost less than waiting for a full wave's bytes).
+  if (!e->launched && !e->cfg.launch_blocks && pending >= quantum / 4 && pending < quantum && quantum >= 1024) return launch_pending(e, total, false);
   if (pending >= quantum) return launch_pending(e, e->launched + pending / quantum * quantum, false);
   // When the caller announced the block count, the last wave is kept small: what is left once the final chunk has
   // arrived is all that stands between the last copied byte and the results.
@@ -1101,10 +1123,11 @@ int ngsq_finish(ngsq_engine* e) {
       uint32_t n_tiles = (n + kCovTile - 1) / kCovTile;
       const int32_t* df = e->d_diff + e->diff_base[c];
       uint64_t* slot = e->d_res + e->cov_slot[c];
-      cov_tile_sums_kernel<<<n_tiles, kCovThreads, 0, s>>>(df, n, slot + COV_TOUCHED, e->d_tile);
-      cov_scan_tiles_kernel<<<1, 1024, 0, s>>>(e->d_tile, n_tiles, slot + COV_TOUCHED);
-      cov_resolve_kernel<<<std::min<uint32_t>(n_tiles, e->n_sm * 4), kCovThreads, 0, s>>>(df, n, e->d_tile, n_tiles, slot);
-      e->other_launches += 3;
+      cov_scan_tiles_kernel<<<1, 1024, 0, s>>>(e->d_tile_sum + e->tile_off[c], e->d_tile, n_tiles, slot + COV_TOUCHED);
+      const uint32_t grid = std::min<uint32_t>(n_tiles, e->n_sm * 4);
+      if (e->cov_bulk) cov_resolve_kernel<true><<<grid, kCovThreads, 0, s>>>(df, n, e->d_tile, n_tiles, slot);
+      else cov_resolve_kernel<false><<<grid, kCovThreads, 0, s>>>(df, n, e->d_tile, n_tiles, slot);
+      e->other_launches += 2;
     }
     CU(cudaGetLastError());
   }

@@ -63,6 +63,8 @@ struct FacetParams {
   const uint8_t* cov_enabled;
   const uint64_t* diff_base; // element offset of each contig's difference array
   int32_t* diff;
+  const uint32_t* tile_off;  // index of each contig's first 4096-position tile in tile_sum
+  int32_t* tile_sum;         // sum of the difference array over every tile, kept as the scatter goes (coverage.cuh)
   const uint32_t* cov_slot;  // word offset of each contig's slot in res
   uint64_t* res;
   uint64_t* qual;            // res + quality offset
@@ -239,17 +241,34 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
     }
 
     // ---- Coverage scatter (coverage.rs:148-180 behind the query filter)
-    if (do_cov && valid && ref >= 0 && pos >= 0 && P.cov_enabled[ref]) {
-      const int64_t L = P.ref_len[ref];
-      const int64_t start = (int64_t)pos + 1, end = start + (int64_t)span - 1;
-      if (start <= L && end >= 1) {
-        P.res[P.cov_slot[ref] + COV_TOUCHED] = 1;
-        if (span) {
-          int32_t* df = P.diff + P.diff_base[ref];
-          atomicAdd(df + start, 1);
-          const int64_t e = end < L ? end : L;
-          atomicAdd(df + e + 1, -1);
-          if (end > L) atomicAdd((unsigned long long*)&P.res[R_NONSENSICAL], (unsigned long long)(end - L));
+    {
+      uint32_t t_up = 0xFFFFFFFFu, t_dn = 0xFFFFFFFFu;  // tiles whose sums take this record's +1 / -1
+      if (do_cov && valid && ref >= 0 && pos >= 0 && P.cov_enabled[ref]) {
+        const int64_t L = P.ref_len[ref];
+        const int64_t start = (int64_t)pos + 1, end = start + (int64_t)span - 1;
+        if (start <= L && end >= 1) {
+          P.res[P.cov_slot[ref] + COV_TOUCHED] = 1;
+          if (span) {
+            int32_t* df = P.diff + P.diff_base[ref];
+            atomicAdd(df + start, 1);
+            const int64_t e = end < L ? end : L;
+            atomicAdd(df + e + 1, -1);
+            if (end > L) atomicAdd((unsigned long long*)&P.res[R_NONSENSICAL], (unsigned long long)(end - L));
+            t_up = P.tile_off[ref] + (uint32_t)(start >> 12);
+            if (e + 1 <= L) t_dn = P.tile_off[ref] + (uint32_t)((e + 1) >> 12);  // position L + 1 lies outside the resolved range
+          }
+        }
+      }
+      // a sorted file sends a warp's 32 records to one or two tiles: one reduction per distinct tile, not per record
+      if (do_cov) {
+        const uint32_t m_up = __ballot_sync(0xFFFFFFFFu, t_up != 0xFFFFFFFFu), m_dn = __ballot_sync(0xFFFFFFFFu, t_dn != 0xFFFFFFFFu);
+        if (t_up != 0xFFFFFFFFu) {
+          const uint32_t peers = __match_any_sync(m_up, t_up);
+          if ((int)lane == __ffs(peers) - 1) atomicAdd(P.tile_sum + t_up, (int)__popc(peers));
+        }
+        if (t_dn != 0xFFFFFFFFu) {
+          const uint32_t peers = __match_any_sync(m_dn, t_dn);
+          if ((int)lane == __ffs(peers) - 1) atomicAdd(P.tile_sum + t_dn, -(int)__popc(peers));
         }
       }
     }

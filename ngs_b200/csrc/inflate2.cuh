@@ -78,12 +78,16 @@ constexpr int kResThreads = 256;
 constexpr int kResWarps = kResThreads / 32;
 constexpr int kResList = 352;  // matches that can start inside 1024 bytes (every match is >= 3 bytes)
 
-// the 8 bytes at s (any alignment) through three aligned 32-bit loads and two funnel shifts: one
+// the 8 bytes at s (any alignment) through up to three aligned 32-bit loads and two funnel shifts: one
 // L1 wavefront per lane per load instead of one per byte (the resolve kernel is L1-wavefront bound)
-__device__ __forceinline__ uint2 load8_unaligned(const uint8_t* s) {
+// (only the first n bytes are used: the third word is fetched only when they reach into it — most matches of BAM data are 3-5 bytes)
+__device__ __forceinline__ uint2 load8_unaligned(const uint8_t* s, uint32_t n) {
   const uint32_t* a = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(s) & ~uintptr_t(3));
-  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
-  const uint32_t w0 = a[0], w1 = a[1], w2 = a[2];
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3);
+  const uint32_t sh = mis * 8;
+  const uint32_t w0 = a[0], w1 = a[1];
+  uint32_t w2 = 0;
+  if (mis + n > 8) w2 = a[2];
   return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
 
@@ -106,7 +110,7 @@ __device__ __forceinline__ void resolve_copy(uint8_t* dst, uint32_t mlen, uint32
   uint32_t D = dist;
   for (uint32_t done = 0; done < mlen;) {
     const uint32_t n = min(min(8u, D), mlen - done);
-    store_bytes(dst + done, load8_unaligned(dst + done - D), n);
+    store_bytes(dst + done, load8_unaligned(dst + done - D, n), n);
     done += n;
     if (D < 8) D <<= 1;
   }

@@ -28,10 +28,13 @@ def _fasta_sequences(fa: bytes):
     return {k: "".join(v).encode() for k, v in out.items()}
 
 
-def engine_edits(bam: bytes, fa: bytes, chunk=None):
+def engine_edits(bam: bytes, fa: bytes, record_facets=True, launch_blocks=0):
+    """record_facets=False is `--only`-style: the one-record cases below carry a mapped pair without mate reference ids,
+    on which the General facet of the reference panics (general.rs:81-83) before Edits ever sees the record."""
     from ngs_b200 import ffi, formats
     b = as_u8(bam)
-    eng = ffi.Engine(flags=ffi.NGSQ_F_RECORD_FACETS | ffi.NGSQ_F_COVERAGE | ffi.NGSQ_F_VERIFY_CRC | ffi.NGSQ_F_EDITS)
+    eng = ffi.Engine(flags=(ffi.NGSQ_F_RECORD_FACETS if record_facets else 0) | ffi.NGSQ_F_COVERAGE | ffi.NGSQ_F_VERIFY_CRC | ffi.NGSQ_F_EDITS,
+                     launch_blocks=launch_blocks)
     hdr = formats.read_header(eng, b)
     eng.set_references([l for _, l in hdr.refs], [1 if formats.is_primary(n) else 0 for n, _ in hdr.refs])
     seqs = _fasta_sequences(fa)
@@ -48,12 +51,13 @@ def engine_edits(bam: bytes, fa: bytes, chunk=None):
 def test_edits_match_oracle(seed):
     bam, bai, fa, _, _ = make_edits_case(seed)
     one, two, vaf, n, _ = oracle_edits(bam, bai, fa)
-    (g_one, g_two, g_vaf, g_n), st = engine_edits(bam, fa)
-    assert g_n == n > 100
-    np.testing.assert_array_equal(g_one, one)
-    np.testing.assert_array_equal(g_two, two)
-    np.testing.assert_array_equal(g_vaf, vaf)
-    assert st["ms_edits"] > 0
+    for launch_blocks in (0, 3):  # one wave, and many: the per-position counters live across waves
+        (g_one, g_two, g_vaf, g_n), st = engine_edits(bam, fa, launch_blocks=launch_blocks)
+        assert g_n == n > 100
+        np.testing.assert_array_equal(g_one, one)
+        np.testing.assert_array_equal(g_two, two)
+        np.testing.assert_array_equal(g_vaf, vaf)
+        assert st["ms_edits"] > 0
 
 
 @pytest.mark.parametrize("case,code,msg", ERRORS, ids=[str(e[1]) for e in ERRORS])
@@ -64,7 +68,7 @@ def test_engine_fails_where_the_oracle_aborts(case, code, msg):
     with pytest.raises(RuntimeError, match=msg):
         oracle_edits(bam, bai, fa)
     with pytest.raises(ffi.NgsqError) as ei:
-        engine_edits(bam, fa)
+        engine_edits(bam, fa, record_facets=False)
     assert ei.value.code == -11  # NGSQ_E_EDITS
 
 
@@ -83,7 +87,7 @@ def test_a_contig_without_a_sequence_fails_only_if_it_holds_records():
     ref = "ACGT" * 1250
     raw = [rec(name="a", flag=0x43, ref=0, pos=100, mapq=9, cigar="20M", seq=ref[100:120])]
     bam, bai = write_bam(REFS, raw)
-    (one, two, vaf, n), _ = engine_edits(bam, f">chr1\n{ref}\n".encode())   # chr2 / chrM have no sequence and no records
+    (one, two, vaf, n), _ = engine_edits(bam, f">chr1\n{ref}\n".encode(), record_facets=False)   # chr2 / chrM have no sequence and no records
     assert n == 1 and one[0] == 1 and int(vaf.sum()) == 20
     with pytest.raises(ffi.NgsqError):
-        engine_edits(bam, b">chr2\nACGT\n")
+        engine_edits(bam, b">chr2\nACGT\n", record_facets=False)
