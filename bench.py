@@ -551,6 +551,8 @@ def main():
             "e2e": None if args.no_e2e else {"value": all_rec / (e2e_ms_max * 1e-3), "unit": "records/s", "h2d_bytes_per_step": int(all_C),
                                              "d2h_bytes_per_step": int(8 * (1216 + 94 * 256 + sum(2052 + L // 50000 + 2 for L in lens))), "ms_per_step": e2e_ms_max,
                                              "ms_tail_after_last_wave_starts": e2e_tail_max,
+                                             "device_ms_total": res_e2e["stats"]["ms_total"], "waves": int(res_e2e["stats"]["waves"]),
+                                             "stage_ms": {k: res_e2e["stats"][k] for k in ["ms_inflate", "ms_inflate_decode", "ms_inflate_resolve", "ms_crc", "ms_scan", "ms_facets", "ms_coverage"]},
                                              "h2d_ceiling_gbs_per_gpu": -neg_h2d_min,
                                              "h2d_ceiling_ms": (C_bytes / 1e9) / (-neg_h2d_min) * 1e3 if neg_h2d_min else None,
                                              "frac_of_h2d_ceiling": ((C_bytes / 1e9) / (-neg_h2d_min) * 1e3) / e2e_ms_max if neg_h2d_min else None,

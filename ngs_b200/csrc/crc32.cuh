@@ -74,9 +74,11 @@ crc32_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ bloc
     const BlockDesc d = blocks[b];
     const uint8_t* p = out + d.out_off;
     const uint32_t n = d.isize;
-    // lane slice [lo, hi): `per` bytes, a multiple of 64; quarter j = [lo + j*q, lo + (j+1)*q) clipped to n.
-    // All quarter starts are multiples of 16 bytes into the block, so every stream has the block's alignment.
-    const uint32_t per = ((n + 31) / 32 + 63) & ~63u;
+    // lane slice [lo, hi): `per` bytes, a multiple of 128; quarter j = [lo + j*q, lo + (j+1)*q) clipped to n.
+    // All quarter starts are multiples of 32 bytes into the block, so every stream has the block's alignment and
+    // consumes whole 32-byte sectors: a lane's loads share no sector with any other lane's, and with 16-byte steps the
+    // second half of every sector had left the (small) L1 before it was asked for — 4.6x DRAM traffic (ncu, profiles/).
+    const uint32_t per = ((n + 31) / 32 + 127) & ~127u;
     const uint32_t q = per / kCrcStreams;
     const uint32_t lo = min(lane * per, n), hi = min(lo + per, n);
     uint32_t s_lo[kCrcStreams], s_hi[kCrcStreams], c[kCrcStreams];
@@ -86,31 +88,36 @@ crc32_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ bloc
       s_hi[j] = min(s_lo[j] + q, hi);
       c[j] = 0xFFFFFFFFu;
     }
-    const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15)) & 15u;
-    // head bytes up to the first 16-byte boundary of each stream
+    const uint32_t head = (32u - (uint32_t)(reinterpret_cast<uintptr_t>(p) & 31)) & 31u;
+    // head bytes up to the first sector boundary of each stream
     for (uint32_t t = 0; t < head; ++t) {
 #pragma unroll
       for (int j = 0; j < kCrcStreams; ++j)
         if (s_lo[j] + t < s_hi[j]) NGSQ_CRC_BYTE(c[j], p[s_lo[j] + t]);
     }
-    // 16-byte chunks, the four streams in lock step (stream 0 is never shorter than the others)
+    // whole sectors, the four streams in lock step (stream 0 is never shorter than the others)
     uint32_t k_n[kCrcStreams];
 #pragma unroll
-    for (int j = 0; j < kCrcStreams; ++j) k_n[j] = s_lo[j] + head < s_hi[j] ? (s_hi[j] - s_lo[j] - head) >> 4 : 0u;
+    for (int j = 0; j < kCrcStreams; ++j) k_n[j] = s_lo[j] + head < s_hi[j] ? (s_hi[j] - s_lo[j] - head) >> 5 : 0u;
     for (uint32_t k = 0; k < k_n[0]; ++k) {
-      uint4 v[kCrcStreams];
+      uint4 v[kCrcStreams][2];
 #pragma unroll
       for (int j = 0; j < kCrcStreams; ++j) {
-        v[j] = make_uint4(0, 0, 0, 0);
-        if (k < k_n[j]) v[j] = *reinterpret_cast<const uint4*>(p + s_lo[j] + head + 16 * k);
+        v[j][0] = v[j][1] = make_uint4(0, 0, 0, 0);
+        if (k < k_n[j]) {
+          const uint4* src = reinterpret_cast<const uint4*>(p + s_lo[j] + head + 32 * k);
+          v[j][0] = src[0];
+          v[j][1] = src[1];
+        }
       }
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
+      for (int w = 0; w < 8; ++w) {
 #pragma unroll
         for (int sh = 0; sh < 32; sh += 8) {
 #pragma unroll
           for (int j = 0; j < kCrcStreams; ++j) {
-            const uint32_t word = w == 0 ? v[j].x : w == 1 ? v[j].y : w == 2 ? v[j].z : v[j].w;
+            const uint4& x = v[j][w >> 2];
+            const uint32_t word = (w & 3) == 0 ? x.x : (w & 3) == 1 ? x.y : (w & 3) == 2 ? x.z : x.w;
             if (k < k_n[j]) NGSQ_CRC_BYTE(c[j], word >> sh);
           }
         }
@@ -119,7 +126,7 @@ crc32_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ bloc
     // tail bytes of each stream
 #pragma unroll
     for (int j = 0; j < kCrcStreams; ++j)
-      for (uint32_t i = s_lo[j] + head + 16 * k_n[j]; i < s_hi[j]; ++i) NGSQ_CRC_BYTE(c[j], p[i]);
+      for (uint32_t i = s_lo[j] + head + 32 * k_n[j]; i < s_hi[j]; ++i) NGSQ_CRC_BYTE(c[j], p[i]);
     // merge the lane's quarters (Horner), then shift the lane's CRC by the bytes that follow its slice
     uint32_t h = 0;
 #pragma unroll

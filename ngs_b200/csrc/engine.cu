@@ -10,6 +10,7 @@
 // the submitting thread never waits for the GPU, the PCIe copy of chunk k+1 overlaps the kernels of wave k, and after
 // the last chunk has arrived only the last (small) wave, the coverage resolve and the result read-back remain.
 #include <dlfcn.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -99,6 +100,9 @@ struct ngsq_engine {
   uint32_t* d_tile_off = nullptr;
   int32_t* d_tile_sum = nullptr;     // sums of the difference arrays per 4096-position tile, maintained by the scatter
   uint64_t tile_total = 0;
+  bool trace = false;                // NGSQ_TRACE=1: per-wave and per-chunk timeline on stderr at ngsq_finish
+  std::vector<double> host_ms;       // host clock at every wave launch (trace)
+  double host_t0 = 0;
   bool cov_bulk = true;              // cov_resolve_kernel<true>: cp.async.bulk staging (NGSQ_COV_BULK=0 selects the direct loads)
 
   // results: [fixed | per-contig coverage slots | quality table, qpos_cap rows]
@@ -130,9 +134,13 @@ struct ngsq_engine {
   uint32_t headroom = 0;
   uint8_t* d_slot[2] = {nullptr, nullptr};
   size_t slot_cap[2] = {0, 0};       // data bytes behind the headroom
-  BlockDesc* d_wblocks[2] = {nullptr, nullptr};
-  uint32_t* d_wcrc[2] = {nullptr, nullptr};
-  uint32_t wtab_cap[2] = {0, 0};
+  // block descriptors and expected CRCs of the whole run, uploaded behind each chunk ON THE COPY STREAM: a wave's
+  // tables are on the device when its bytes are, and no other stream ever queues a copy behind the chunk copies
+  BlockDesc* d_blocks_all = nullptr;
+  uint32_t* d_crc_all = nullptr;
+  uint32_t blocks_all_cap = 0;
+  struct PinSlab { uint8_t* p; size_t cap, used; };
+  std::vector<PinSlab> pin_slabs;    // pinned staging of those uploads (lives until ngsq_reset)
   uint32_t *d_wstatus = nullptr, *d_first = nullptr, *d_landed = nullptr, *d_count = nullptr;
   uint64_t* d_base = nullptr;
   uint32_t scan_cap = 0;
@@ -148,8 +156,6 @@ struct ngsq_engine {
   uint64_t* h_prog = nullptr;        // pinned ring: {rec_base, wave_rec} after each wave's scan (ngsq_progress)
   uint32_t prog_seen = 0;            // waves whose probe has been consumed
   uint64_t prog_records = 0;
-  struct Staging { BlockDesc* blocks = nullptr; uint32_t* crc = nullptr; uint32_t cap = 0; cudaEvent_t done = nullptr; bool busy = false; };
-  Staging staging[3];
   CrcTables* d_crc_tables = nullptr;
 
   // shard range (virtual offsets -> blocks, resolved as the blocks arrive)
@@ -326,6 +332,50 @@ int append_blocks(ngsq_engine* e, const ngsq_block* blk, uint32_t n, uint64_t de
   return NGSQ_OK;
 }
 
+// pinned bytes that stay put until ngsq_reset
+void* pin_alloc(ngsq_engine* e, size_t bytes) {
+  bytes = (bytes + 63) & ~size_t(63);
+  for (auto& ps : e->pin_slabs)
+    if (ps.used + bytes <= ps.cap) { void* r = ps.p + ps.used; ps.used += bytes; return r; }
+  const size_t cap = std::max<size_t>(bytes, (size_t)8 << 20);
+  uint8_t* p = nullptr;
+  if (cudaHostAlloc((void**)&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  e->pin_slabs.push_back({p, cap, bytes});
+  return p;
+}
+
+// Descriptors and expected CRCs of blocks [first, end) follow their chunk on the copy stream.
+int upload_descriptors(ngsq_engine* e, uint32_t first, uint32_t end) {
+  if (end <= first) return NGSQ_OK;
+  if (end > e->blocks_all_cap) {
+    // the table is sized by reserve_blocks; without it, it doubles (rare: everything in flight is awaited first)
+    CU(cudaStreamSynchronize(e->s_copy));
+    CU(cudaStreamSynchronize(e->s_comp));
+    CU(cudaStreamSynchronize(e->s_aux));
+    const uint32_t cap = std::max<uint32_t>(end + end / 2, std::max<uint32_t>(e->cfg.reserve_blocks, 1u << 18));
+    BlockDesc* nb = nullptr;
+    uint32_t* nc = nullptr;
+    if (cudaMalloc(&nb, (size_t)cap * sizeof(BlockDesc)) != cudaSuccess || cudaMalloc(&nc, (size_t)cap * 4) != cudaSuccess)
+      return fail(e, NGSQ_E_NOMEM, "cudaMalloc block tables (%u blocks)", cap);
+    if (first) {
+      CU(cudaMemcpy(nb, e->d_blocks_all, (size_t)first * sizeof(BlockDesc), cudaMemcpyDeviceToDevice));
+      CU(cudaMemcpy(nc, e->d_crc_all, (size_t)first * 4, cudaMemcpyDeviceToDevice));
+    }
+    if (e->d_blocks_all) cudaFree(e->d_blocks_all);
+    if (e->d_crc_all) cudaFree(e->d_crc_all);
+    e->d_blocks_all = nb; e->d_crc_all = nc; e->blocks_all_cap = cap;
+  }
+  const uint32_t n = end - first;
+  BlockDesc* hb = (BlockDesc*)pin_alloc(e, (size_t)n * sizeof(BlockDesc));
+  uint32_t* hc = (uint32_t*)pin_alloc(e, (size_t)n * 4);
+  if (!hb || !hc) return fail(e, NGSQ_E_NOMEM, "cudaHostAlloc block tables (%u blocks)", n);
+  memcpy(hb, e->h_blocks.data() + first, (size_t)n * sizeof(BlockDesc));
+  memcpy(hc, e->h_crc.data() + first, (size_t)n * 4);
+  CU(cudaMemcpyAsync(e->d_blocks_all + first, hb, (size_t)n * sizeof(BlockDesc), cudaMemcpyHostToDevice, e->s_copy));
+  CU(cudaMemcpyAsync(e->d_crc_all + first, hc, (size_t)n * 4, cudaMemcpyHostToDevice, e->s_copy));
+  return NGSQ_OK;
+}
+
 // first block with file offset >= co among blocks [0, n)
 uint32_t block_lower_bound(const ngsq_engine* e, uint32_t n, uint64_t co) {
   uint32_t lo = 0, hi = n;
@@ -406,16 +456,9 @@ int ensure_wave_buffers(ngsq_engine* e, int s, uint32_t n, uint64_t bytes) {
     if ((rc = fresh(e, e->d_slot[s], (size_t)e->headroom + want + 64, "inflated slot"))) return rc;
     e->slot_cap[s] = want;
   }
-  if (n > e->wtab_cap[s]) {
-    if ((rc = quiesce())) return rc;
-    const uint32_t cap = std::max<uint32_t>(n + n / 8, std::min<uint32_t>(launch_quantum(e), std::max<uint32_t>(e->cfg.reserve_blocks, 64u)));
-    if ((rc = fresh(e, e->d_wblocks[s], cap, "block table"))) return rc;
-    if ((rc = fresh(e, e->d_wcrc[s], cap, "crc table"))) return rc;
-    e->wtab_cap[s] = cap;
-  }
   if (n > e->scan_cap) {
     if ((rc = quiesce())) return rc;
-    const uint32_t cap = std::max(e->wtab_cap[0], e->wtab_cap[1]);
+    const uint32_t cap = std::max<uint32_t>(n + n / 8, std::min<uint32_t>(launch_quantum(e), std::max<uint32_t>(e->cfg.reserve_blocks, 64u)));
     if ((rc = fresh(e, e->d_wstatus, cap, "status"))) return rc;
     if ((rc = fresh(e, e->d_first, cap, "scan tables"))) return rc;
     if ((rc = fresh(e, e->d_landed, cap, "scan tables"))) return rc;
@@ -458,35 +501,18 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
   if (rc) return rc;
   const uint32_t wi = (uint32_t)e->waves.size();
   const int s = (int)(wi & 1);
+  if (e->trace) {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    if (!wi) e->host_t0 = now;
+    e->host_ms.push_back(now - e->host_t0);
+  }
   cudaStream_t st = e->s_comp;
   const uint64_t out0 = e->h_blocks[b0].out_off;
   const uint64_t bytes = e->h_blocks[b1 - 1].out_off + e->h_blocks[b1 - 1].isize - out0;
   // slot s and its tables were last used by wave wi - 2: its CRC kernel (own stream) must be done with them
   if (wi >= 2) CU(cudaStreamWaitEvent(st, e->waves[wi - 2].crc_end, 0));
   if ((rc = ensure_wave_buffers(e, s, n, bytes))) return rc;
-  // pinned staging of the wave's tables (a pageable source would make the "async" copy wait for the stream)
-  ngsq_engine::Staging& sg = e->staging[wi % 3];
-  if (sg.busy) CU(cudaEventSynchronize(sg.done));
-  if (n > sg.cap) {
-    if (sg.blocks) cudaFreeHost(sg.blocks);
-    if (sg.crc) cudaFreeHost(sg.crc);
-    sg.blocks = nullptr; sg.crc = nullptr;
-    const uint32_t cap = std::max<uint32_t>(n, e->wtab_cap[s]);
-    if (cudaHostAlloc((void**)&sg.blocks, (size_t)cap * sizeof(BlockDesc), cudaHostAllocDefault) != cudaSuccess ||
-        cudaHostAlloc((void**)&sg.crc, (size_t)cap * 4, cudaHostAllocDefault) != cudaSuccess)
-      return fail(e, NGSQ_E_NOMEM, "cudaHostAlloc wave tables (%u blocks)", cap);
-    sg.cap = cap;
-    if (!sg.done) CU(cudaEventCreateWithFlags(&sg.done, cudaEventDisableTiming));
-  }
-  for (uint32_t i = 0; i < n; ++i) {
-    sg.blocks[i] = e->h_blocks[b0 + i];
-    sg.blocks[i].out_off -= out0;
-    sg.crc[i] = e->h_crc[b0 + i];
-  }
-  CU(cudaMemcpyAsync(e->d_wblocks[s], sg.blocks, (size_t)n * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(e->d_wcrc[s], sg.crc, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaEventRecord(sg.done, st));
-  sg.busy = true;
   // the compressed bytes of the wave: wait for the copy of the last chunk it reads
   for (const auto& c : e->chunks)
     if (c.blocks_end >= b1) { CU(cudaStreamWaitEvent(st, c.copied, 0)); break; }
@@ -494,9 +520,11 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
   if ((rc = new_wave_events(e, w))) return rc;
   w.b1 = b1;
   uint8_t* slot = e->d_slot[s];
-  uint8_t* out = slot + e->headroom;
+  // descriptors carry offsets in the whole inflated stream; the wave's first block lands right behind the headroom
+  uint8_t* out = slot + e->headroom - out0;
+  const BlockDesc* wblocks = e->d_blocks_all + b0;
   CU(cudaEventRecord(w.begin, st));
-  rc = launch_inflate(e, e->d_wblocks[s], n, out, e->d_queue, e->d_wstatus, e->d_bitmap, st, w.decoded_from, w.decoded);
+  rc = launch_inflate(e, wblocks, n, out, e->d_queue, e->d_wstatus, e->d_bitmap, st, w.decoded_from, w.decoded);
   if (rc) return rc;
   e->other_launches += 1;  // resolve kernel (the decode kernel is counted as the inflate launch)
   CU(cudaEventRecord(w.resolved, st));
@@ -506,7 +534,7 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
   CU(cudaEventRecord(w.crc_begin, e->s_aux));
   if (e->cfg.flags & NGSQ_F_VERIFY_CRC) {
     const uint32_t grid = std::min<uint32_t>((n + kCrcThreads / 32 - 1) / (kCrcThreads / 32), (uint32_t)e->n_sm * 6);
-    crc32_kernel<<<grid, kCrcThreads, kCrcSmem, e->s_aux>>>(out, e->d_wblocks[s], e->d_wcrc[s], n, e->d_crc_tables, &e->d_state->crc_bad);
+    crc32_kernel<<<grid, kCrcThreads, kCrcSmem, e->s_aux>>>(out, wblocks, e->d_crc_all + b0, n, e->d_crc_tables, &e->d_state->crc_bad);
     CU(cudaGetLastError());
     e->other_launches++;
   }
@@ -527,7 +555,7 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
     return NGSQ_OK;
   }
   WaveParams W{};
-  W.d = slot; W.blocks = e->d_wblocks[s]; W.status = e->d_wstatus; W.n_blocks = n; W.first_global = b0; W.headroom = e->headroom;
+  W.d = slot; W.out0 = out0; W.blocks = wblocks; W.status = e->d_wstatus; W.n_blocks = n; W.first_global = b0; W.headroom = e->headroom;
   W.first_wave = e->start_block >= b0 ? 1u : 0u;
   W.final_wave = final_wave ? 1u : 0u;
   W.n_ref = (int32_t)e->n_ref;
@@ -559,7 +587,7 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
   const bool cov_n = (e->cfg.flags & NGSQ_F_COVERAGE) && e->cfg.max_records;
   if (e->cfg.flags & (NGSQ_F_RECORD_FACETS | NGSQ_F_COVERAGE)) {
     FacetParams P{};
-    P.d = slot; P.rec = e->d_rec; P.st = e->d_state; P.st_w = e->d_state; P.blocks = e->d_wblocks[s]; P.headroom = e->headroom;
+    P.d = slot; P.rec = e->d_rec; P.st = e->d_state; P.st_w = e->d_state; P.blocks = wblocks; P.headroom = e->headroom; P.out0 = out0;
     P.cov_scatter = cov_n ? 0u : 1u;
     P.max_records = e->cfg.max_records; P.gc_seed = e->cfg.gc_seed; P.n_ref = (int32_t)e->n_ref; P.flags = e->cfg.flags;
     P.ref_len = e->d_ref_len; P.cov_enabled = e->d_cov_enabled; P.diff_base = e->d_diff_base; P.diff = e->d_diff; P.cov_slot = e->d_cov_slot;
@@ -695,6 +723,7 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   ne->device = device;
   if (cfg) memcpy(&ne->cfg, cfg, std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(ngsq_config), sizeof(ngsq_config)));
   if (!ne->cfg.flags) ne->cfg.flags = NGSQ_F_RECORD_FACETS | NGSQ_F_COVERAGE;
+  if (const char* v = getenv("NGSQ_TRACE")) ne->trace = atoi(v) != 0;
   if (const char* v = getenv("NGSQ_COV_BULK")) ne->cov_bulk = atoi(v) != 0;  // A/B switch for profiles/ (default: the measured winner)
   ne->headroom = ne->cfg.carry_bytes ? ((ne->cfg.carry_bytes + 63u) & ~63u) : kDefaultHeadroom;
   e = ne;
@@ -747,16 +776,12 @@ void ngsq_destroy(ngsq_engine* e) {
   for (auto& p : e->waves) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.resolved, p.scan_end, p.facets_end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
   for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_d, e->ev_e, e->ev_f, e->ev_g}) if (ev) cudaEventDestroy(ev);
   void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_tile_off, e->d_tile_sum, e->d_res, e->d_slot[0], e->d_slot[1],
-                  e->d_wblocks[0], e->d_wblocks[1], e->d_wcrc[0], e->d_wcrc[1], e->d_wstatus, e->d_first, e->d_landed, e->d_count, e->d_base,
+                  e->d_blocks_all, e->d_crc_all, e->d_wstatus, e->d_first, e->d_landed, e->d_count, e->d_base,
                   e->d_bitmap, e->d_rec, e->d_mark, e->d_queue, e->d_state, e->d_crc_tables};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (e->h_state) cudaFreeHost(e->h_state);
   if (e->h_prog) cudaFreeHost(e->h_prog);
-  for (auto& sg : e->staging) {
-    if (sg.blocks) cudaFreeHost(sg.blocks);
-    if (sg.crc) cudaFreeHost(sg.crc);
-    if (sg.done) cudaEventDestroy(sg.done);
-  }
+  for (auto& ps : e->pin_slabs) cudaFreeHost(ps.p);
   for (void* p : e->ed_allocs) cudaFree(p);
   for (void* p : {(void*)e->d_ed_contigs, (void*)e->d_ed_refs, (void*)e->d_ed_alts, (void*)e->d_ed_res}) if (p) cudaFree(p);
   for (void* p : e->ft_allocs) cudaFree(p);
@@ -781,10 +806,11 @@ int ngsq_reset(ngsq_engine* e) {
   e->waves.clear();
   e->h_blocks.clear(); e->h_crc.clear();
   for (auto& sg : e->comp_segs) { sg.used = 0; sg.blocks_end = 0; }
-  for (auto& sg : e->staging) sg.busy = false;
+  for (auto& ps : e->pin_slabs) ps.used = 0;
   e->out_used = 0; e->comp_bytes_total = 0; e->other_launches = 0;
   e->start_resolved = e->end_resolved = false;
   e->prog_seen = 0; e->prog_records = 0;
+  e->host_ms.clear();
   // rows of the quality table the next run has to clear; a run that never reached ngsq_finish may have touched any
   e->qpos_dirty = (e->run_started && !e->finished) ? e->qpos_cap : std::max(e->qpos_dirty, e->h_qpos);
   e->run_started = false; e->finished = false;
@@ -1027,12 +1053,15 @@ int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t fil
   rc = acquire_comp(e, nbytes, &dst);
   if (rc) return rc;
   CU(cudaMemcpyAsync(dst, bgzf, nbytes, cudaMemcpyHostToDevice, e->s_copy));
-  cudaEvent_t ev;
-  CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CU(cudaEventRecord(ev, e->s_copy));
   e->comp_bytes_total += nbytes;
+  const uint32_t first_new = (uint32_t)e->h_blocks.size();
   rc = append_blocks(e, blk.data(), n, (uint64_t)(uintptr_t)dst, file_off);
-  if (rc) { cudaEventDestroy(ev); return rc; }
+  if (rc) return rc;
+  rc = upload_descriptors(e, first_new, (uint32_t)e->h_blocks.size());
+  if (rc) return rc;
+  cudaEvent_t ev;
+  CU(cudaEventCreateWithFlags(&ev, e->trace ? cudaEventDefault : cudaEventDisableTiming));
+  CU(cudaEventRecord(ev, e->s_copy));
   e->chunks.push_back({ev, (uint32_t)e->h_blocks.size()});
   e->comp_segs.back().blocks_end = (uint32_t)e->h_blocks.size();
   // inflate in whole waves; the copy of the next chunk overlaps the kernels of this one
@@ -1092,8 +1121,15 @@ int ngsq_submit_device(ngsq_engine* e, const void* dev_bgzf, size_t nbytes, cons
   const ngsq_block& last = blocks[n_blocks - 1];
   if (last.coffset + last.csize - blocks[0].coffset > nbytes) return fail(e, NGSQ_E_TRUNCATED, "block table runs past the device buffer");
   e->comp_bytes_total += nbytes;
+  const uint32_t first_new = (uint32_t)e->h_blocks.size();
   rc = append_blocks(e, blocks, n_blocks, (uint64_t)(uintptr_t)dev_bgzf, blocks[0].coffset);
   if (rc) return rc;
+  rc = upload_descriptors(e, first_new, (uint32_t)e->h_blocks.size());
+  if (rc) return rc;
+  cudaEvent_t ev;
+  CU(cudaEventCreateWithFlags(&ev, e->trace ? cudaEventDefault : cudaEventDisableTiming));
+  CU(cudaEventRecord(ev, e->s_copy));
+  e->chunks.push_back({ev, (uint32_t)e->h_blocks.size()});
   // resident data: every wave is enqueued at once (the caller's buffer is used in place)
   return launch_pending(e, (uint32_t)e->h_blocks.size(), false);
 }
@@ -1186,6 +1222,18 @@ int ngsq_finish(ngsq_engine* e) {
   if (!e->waves.empty()) cudaEventElapsedTime(&st.ms_tail, e->waves.back().begin, e->ev_f);
   st.waves = (uint32_t)e->waves.size();
   st.other_launches = e->other_launches;
+  if (e->trace) {
+    auto at = [&](cudaEvent_t ev) { float ms = 0; cudaEventElapsedTime(&ms, e->ev_start, ev); return ms; };
+    fprintf(stderr, "[ngsq trace] %zu chunks, %zu waves, total %.1f ms (ms since the first submit)\n", e->chunks.size(), e->waves.size(), st.ms_total);
+    for (size_t i = 0; i < e->chunks.size(); ++i)
+      if (i % 8 == 7 || i + 1 == e->chunks.size()) fprintf(stderr, "[ngsq trace] chunk %3zu copied at %8.1f (blocks < %u)\n", i, at(e->chunks[i].copied), e->chunks[i].blocks_end);
+    for (size_t i = 0; i < e->waves.size(); ++i) {
+      const auto& w = e->waves[i];
+      fprintf(stderr, "[ngsq trace] wave %2zu blocks<%7u host %7.1f | begin %7.1f decode %7.1f..%7.1f resolved %7.1f scan %7.1f facets %7.1f | crc %7.1f..%7.1f\n", i, w.b1,
+              i < e->host_ms.size() ? e->host_ms[i] : -1.0, at(w.begin), at(w.decoded_from), at(w.decoded), at(w.resolved), at(w.scan_end), at(w.facets_end), at(w.crc_begin), at(w.crc_end));
+    }
+    fprintf(stderr, "[ngsq trace] coverage %.1f..%.1f end %.1f\n", at(e->ev_d), at(e->ev_e), at(e->ev_f));
+  }
   // verdicts, in the order the reference would meet them: a block that does not inflate, a block whose CRC32 is wrong
   // (its garbage bytes break the record chain too: CRC first), then the record chain, then the records
   if (R.fatal & kFatalInflate) {

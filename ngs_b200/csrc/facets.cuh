@@ -55,6 +55,7 @@ struct FacetParams {
   const BlockDesc* blocks;   // the wave's blocks (file offsets for virtual offsets)
   uint32_t headroom;
   uint32_t cov_scatter;      // 1: this kernel scatters coverage (0 with `-n`: cov_n.cuh applies the second pass's counter)
+  uint64_t out0;             // offset of the wave's first block in the whole inflated stream
   uint64_t max_records;      // 0 = all
   uint64_t gc_seed;
   int32_t n_ref;
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
           // the record's BGZF virtual offset: its block's file offset and its offset in that block
           const uint32_t t = (uint32_t)(rv >> 40);
           uint64_t voff = P.st->carry_voff;
-          if (t) { const BlockDesc& bd = P.blocks[t - 1]; voff = (bd.coff << 16) | ((rv & kRecOffMask) - P.headroom - bd.out_off); }
+          if (t) { const BlockDesc& bd = P.blocks[t - 1]; voff = (bd.coff << 16) | ((rv & kRecOffMask) - P.headroom - (bd.out_off - P.out0)); }
           gc_off = (uint32_t)(((splitmix64_dev(P.gc_seed ^ voff) >> 32) * (uint64_t)(lseq - 100)) >> 32);
         }
       }

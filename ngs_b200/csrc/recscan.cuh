@@ -77,7 +77,8 @@ struct RunState {
 
 struct WaveParams {
   const uint8_t* d;         // slot base
-  const BlockDesc* blocks;  // the wave's blocks; out_off is relative to d + headroom
+  uint64_t out0;            // offset of the wave's first block in the whole inflated stream
+  const BlockDesc* blocks;  // the wave's blocks; block b sits at d + headroom + (out_off - out0)
   const uint32_t* status;   // inflate verdict per block
   uint32_t n_blocks;
   uint32_t first_global;    // global index of blocks[0]
@@ -109,7 +110,7 @@ __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p) {
 __device__ __forceinline__ uint64_t wave_root(const WaveParams& W) {
   return W.first_wave ? W.start_off : (uint64_t)W.headroom - W.st->carry_len;  // carry_len is 0 in the first wave
 }
-__device__ __forceinline__ uint64_t block_lo(const WaveParams& W, uint32_t b) { return W.headroom + W.blocks[b].out_off; }
+__device__ __forceinline__ uint64_t block_lo(const WaveParams& W, uint32_t b) { return W.headroom + (W.blocks[b].out_off - W.out0); }
 __device__ __forceinline__ bool wave_dead(const RunState* st) { return st->fatal || st->end_reached; }
 
 // Header plausibility of a record starting at slot offset `off`; [.., d_end) is the data a record of this wave may
