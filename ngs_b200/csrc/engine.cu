@@ -1066,15 +1066,11 @@ int ngsq_submit(ngsq_engine* e, const uint8_t* bgzf, size_t nbytes, uint64_t fil
   e->comp_segs.back().blocks_end = (uint32_t)e->h_blocks.size();
   // inflate in whole waves; the copy of the next chunk overlaps the kernels of this one
   const uint32_t quantum = launch_quantum(e), total = (uint32_t)e->h_blocks.size(), pending = total - e->launched;
-  // The GPU work of a shard takes about as long as its PCIe copy, so it must start early: the FIRST wave is a quarter of
-  // the others (the lanes it leaves idle for one round cost less than waiting for a full wave's bytes).
-  if (!e->launched && !e->cfg.launch_blocks && pending >= quantum / 4 && pending < quantum && quantum >= 1024) return launch_pending(e, total, false);
+  // Every wave costs one decode round (~18 ms on a B200 whatever its size), and at 55 GB/s of PCIe the GPU work of a
+  // shard takes as long as its copy: fewer, full waves win.  A smaller first wave (earlier start) and a cut-off last wave
+  // (shorter tail) were measured and each cost a round more than it saved (profiles/round2_e2e_timeline.md); callers
+  // whose copies are the slower side can still ask for a short tail with ngsq_flush.
   if (pending >= quantum) return launch_pending(e, e->launched + pending / quantum * quantum, false);
-  // When the caller announced the block count, the last wave is kept small: what is left once the final chunk has
-  // arrived is all that stands between the last copied byte and the results.
-  const uint32_t tail = std::max<uint32_t>(quantum / 8, 1);
-  if (e->cfg.reserve_blocks && !e->cfg.launch_blocks && pending > tail && total < e->cfg.reserve_blocks && e->cfg.reserve_blocks - total <= tail)
-    return launch_pending(e, total, false);
   return NGSQ_OK;
 }
 

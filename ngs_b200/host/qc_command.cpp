@@ -132,7 +132,6 @@ class ChunkReader {
       if (ngsq_bgzf_walk(begin, n, file_off, nullptr, 0, &nb, &used)) throw std::runtime_error("malformed BGZF framing");
       if (last && used != n) throw std::runtime_error("truncated BGZF block at end of file");
       if (used) {
-        if (last) check(e, ngsq_flush(e));  // what remains after the last copied byte is one small wave
         check(e, ngsq_submit(e, begin, used, file_off));
         used_by[bi] = (int32_t)submits++;
         file_off += used;
