@@ -1,46 +1,34 @@
-// K2 — per-lane DEFLATE decoder with the LZ77 copies fused in: ONE BGZF block per lane, 32 blocks per warp
-// instruction (reference: the inflate noodles-bgzf/miniz_oxide perform under bam::Reader,
+// K2a — per-lane DEFLATE symbol decoder: ONE BGZF block per lane, 32 blocks per warp instruction
+// (reference: the inflate noodles-bgzf/miniz_oxide perform under bam::Reader,
 // src/utils/formats/bam.rs:41-44; format = RFC 1951 inside the BGZF framing of SAM spec 4.1).
 //
-// Round 1 split inflate in two kernels (Huffman decode with in-place match tokens, then a warp-per-block resolve
-// pass).  The resolve pass turned out to be bound by its byte-granular stores — one L2 transaction per output
-// byte, 27 G of them per 100 M records — and re-read the whole stream from DRAM.  Here every lane finishes its
-// own block: output bytes — literals and match bytes alike — go through one 16-byte accumulator and leave as
-// 128-bit stores, and a match is copied by the lane that decoded it, in PIECES of at most 8 bytes whose source
-// load is issued one loop iteration before its bytes are appended:
-//   iteration i     decode a symbol; for a match, issue the (up to three) aligned 32-bit loads that cover the
-//                   first piece's source and park the raw words;
-//   iteration i+1   funnel-shift the parked words (by then the load has had a whole iteration — ~1500 cycles of
-//                   the warp's other work — to return from L2 / HBM), append the piece, go on decoding; a match
-//                   longer than a piece keeps its lane copying (one piece per iteration) instead of decoding.
-// Everything a lane reads back it wrote itself, in program order, so no synchronisation exists anywhere:
-//   * bytes of completed 16-byte chunks are in memory;
-//   * bytes of the open chunk are stored (a full 16-byte store, the unwritten tail as zeros — the lane owns the
-//     whole chunk) right before a load whose source reaches into it;
-//   * a piece never exceeds its distance (overlapping runs double their period per piece, as memmove-free
-//     LZ77 copies do), so a source never includes bytes of its own piece.
-// On BAM data 96 % of the matches are one piece (81 % are 3-4 bytes), so a lane spends 4-5 % more iterations than
-// it has symbols.
+// Huffman decoding never looks at the LZ77 window, so it is separated from the match copies:
+//   * this decoder writes literals to their final positions (gathered into aligned 16-byte
+//     chunks) and, for every match, a 3-byte token IN PLACE at the match destination
+//     ((len-3) | (dist-1) << 8) plus one bit in a per-block bitmap (bit = match starts here);
+//   * the warp-per-block resolve kernel (inflate2.cuh) then walks the bitmap in stream order and
+//     performs the copies.
 //
 // Decoding is CANONICAL and branch-free, not table-driven: the code length of the next symbol is
 // 1 + the number of per-length limits (left-aligned end of each length's code range, 16 x u16
 // packed in 8 registers) that the next 15 bits reach, counted with packed 16-bit subtractions; the
 // symbol is sorted[code + base[len]].  Every lane executes the same instructions whatever its code
-// length (with a LUT + slow path a warp pays for both on nearly every symbol), and the per-lane
-// shared-memory footprint is 396 bytes — shared memory is what bounds the resident decoders per SM (18 warps).
+// length (with a LUT + slow path a warp pays for both on nearly every symbol: ncu, profiles/), and
+// the per-lane shared-memory footprint is 0.6 KB instead of 1.2-1.7 KB — shared memory is what
+// bounds the number of resident decoders per SM.
 //
 // Everything in this file is scalar per-lane code with no warp intrinsics, so the same source
 // also compiles for the host: tools/inflate_model.cpp runs it against zlib as a CPU model of the
 // kernel (test tooling only; the product has no CPU path).
 //
-// Per-lane shared-memory slab (kSlabBytes; 99 words, odd, so that equal indices of neighbouring lanes fall
-// into different banks):
-//   SL_LLBT  u32 ll_bt[15]       per code length 1..15: (index of first symbol - first code) & 0xFFFF
-//                                | (index of the first symbol >= 256 of that length) << 16
+// Per-lane shared-memory slab (kSlabBytes, odd number of words so that equal indices of
+// neighbouring lanes fall into different banks):
 //   SL_LLS   u8  ll_sorted[288]  literal/length symbols (& 255) in canonical order
 //                                (while a dynamic header is parsed: the code-length-code LUT)
-//   SL_DB    u8  d_base[15]      per distance code length: (index of first symbol - first code) mod 32
+//   SL_LLBT  u32 ll_bt[16]       per code length: (index of first symbol - first code) & 0xFFFF
+//                                | (index of the first symbol >= 256 of that length) << 16
 //   SL_DS    u8  d_sorted[32]    distance symbols in canonical order
+//   SL_DB    i16 d_base[16]
 // The 4-bit code lengths of a dynamic header and the build counters live in per-thread local
 // memory (header() only; lanes of a warp parse their headers in lock step, so those accesses
 // coalesce): shared memory is spent on what the symbol loop reads.
@@ -58,20 +46,41 @@
 
 namespace ngsq {
 
+// Symbol-loop variants (bit mask; build with -DNGSQ_DEC_VARIANT=n).  Every variant decodes bit-identically in the host
+// model (tests/test_inflate_model.py) and on the GPU (tools/ab_decode.sh runs the parity tests per variant).  Measured on
+// a B200, 30 M records (profiles/round2_ab_inflate_variants.md): 0 -> 36.6 ms, 7 -> 32.5, 15 -> 32.1, 31 -> 33.1; the
+// default is 15.
+//   1  length / distance bases and extra-bit counts from a 64-word table (per-CTA shared memory) instead of arithmetic
+//   2  match bitmap word flushed by a predicated store instead of a branch
+//   4  emit(): chunk stores predicated, accumulator updates by selects (no divergent flush paths, no phi copies)
+//   8  396-byte slab (u8 distance bases, exact-size symbol arrays): 18 decoder warps per SM instead of 17
+//  16  code length = 1 - (signed byte dot product of the sign-replicated flag bytes): 4 PRMT + 4 IDP.4A instead of
+//      4 PRMT + 7 logic ops + POPC, twice per match
+#ifndef NGSQ_DEC_VARIANT
+#define NGSQ_DEC_VARIANT 15
+#endif
+
+#if NGSQ_DEC_VARIANT & 8
 // ll_bt[15] and d_base[15] are indexed by length - 1 (length 16 = invalid code reads the neighbouring bytes of the
 // slab; the block is failed anyway), distance bases are kept mod 32 in bytes: 60 + 288 + 15 + 32 = 395 -> 99 words
 constexpr int SL_LLBT = 0, SL_LLS = 60, SL_DB = 348, SL_DS = 363;
 constexpr int kSlabBytes = 396;
 constexpr int kLenIndexBias = 1;
 typedef uint8_t dbase_t;
-constexpr uint32_t kPieceBytes = 8;  // bytes of a match copied per loop iteration
+#else
+constexpr int SL_LLS = 0, SL_LLBT = 288, SL_DS = 352, SL_DB = 384;
+constexpr int kSlabBytes = 416 + 4;
+constexpr int kLenIndexBias = 0;
+typedef int16_t dbase_t;
+#endif
+constexpr uint32_t kBitmapWords = 2048;  // per BGZF block: one bit per inflated byte (<= 65536)
 
 enum : uint32_t { kBlkOk = 0, kBlkBadStream = 1, kBlkIsize = 2, kBlkOverrun = 3 };
 enum : int { LS_HEADER = 0, LS_DECODE = 1, LS_IDLE = 2 };
 
 struct BlockDesc {
   uint64_t in_off;   // absolute device address of the DEFLATE payload
-  uint64_t out_off;  // offset of this block's first inflated byte in the whole stream (kernels get `out` shifted by the wave's first offset)
+  uint64_t out_off;  // offset of this block's first inflated byte in its wave (relative to the `out` the kernels get)
   uint32_t clen;     // DEFLATE payload length
   uint32_t isize;    // expected inflated size
   uint64_t coff;     // file offset of the BGZF block (virtual offsets of its records)
@@ -89,8 +98,8 @@ NGSQ_HD uint32_t brev32(uint32_t x) {
 #endif
 }
 
-// entry i < 32: length symbol 257 + i -> (match length - 3 base) | extra bits << 8;
-// entry 32 + i: distance symbol i -> (distance - 1 base) | extra bits << 16   (64 words of per-CTA shared memory)
+// variant 1: entry i < 32: length symbol 257 + i -> (match length - 3 base) | extra bits << 8;
+// entry 32 + i: distance symbol i -> (distance - 1 base) | extra bits << 16
 NGSQ_HD uint32_t base_lut_entry(uint32_t i) {
   if (i < 32) {
     const uint32_t li = i > 28 ? 28 : i;
@@ -104,10 +113,48 @@ NGSQ_HD uint32_t base_lut_entry(uint32_t i) {
   return b | (deb << 16);
 }
 
+NGSQ_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {  // PRMT, default mode (selector bit 3: replicate the sign)
+#if defined(__CUDA_ARCH__)
+  uint32_t r;  // not __byte_perm(): the intrinsic masks each selector nibble to 3 bits and drops the sign mode
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+#else
+  const uint64_t v = (uint64_t)a | ((uint64_t)b << 32);
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t n = (sel >> (4 * i)) & 15;
+    uint32_t byte = (uint32_t)(v >> (8 * (n & 7))) & 255;
+    if (n & 8) byte = (byte & 128) ? 255 : 0;
+    r |= byte << (8 * i);
+  }
+  return r;
+#endif
+}
+NGSQ_HD int dp4a_s8(uint32_t a, uint32_t b, int c) {  // IDP.4A, signed bytes
+#if defined(__CUDA_ARCH__)
+  return __dp4a((int)a, (int)b, c);
+#else
+  for (int i = 0; i < 4; ++i) c += (int)(int8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i));
+  return c;
+#endif
+}
+
+struct Quad { uint32_t x, y, z, w; };
+
+NGSQ_HD Quad ld_in128(const uint8_t* p) {  // p is 16-byte aligned
+  Quad q;
+#if defined(__CUDA_ARCH__)
+  uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  q.x = v.x; q.y = v.y; q.z = v.z; q.w = v.w;
+#else
+  memcpy(&q, p, 16);
+#endif
+  return q;
+}
+
 struct InflateCounters {  // host model only
   uint64_t symbols = 0, literals = 0, matches = 0, match_bytes = 0, headers = 0, stored = 0, fixed = 0, chunk_stores = 0,
-           edge_stores = 0, pieces = 0, copy_iterations = 0, open_chunk_stores = 0, ll_len_hist[17] = {0}, d_len_hist[17] = {0},
-           match_len_hist[260] = {0};
+           edge_stores = 0, ll_len_hist[17] = {0}, d_len_hist[17] = {0};
 };
 
 struct Lane {
@@ -127,19 +174,17 @@ struct Lane {
   const uint8_t* in_end;
   // output, in "aligned coordinates": q = block-relative position + (address of the block & 15)
   uint8_t* obase;           // 16-byte aligned address of coordinate 0
-  uint32_t q, q0, qend;     // q: everything before it has been appended (to the accumulator or to memory)
-  uint64_t acc_lo, acc_hi;  // bytes [q & ~15, q) of the open 16-byte chunk; zero beyond
-  // the piece that will be appended at the top of the next iteration: a literal (pw0 = the byte) or up to
-  // kPieceBytes of a match, as the raw aligned words of its source (the load may still be in flight)
-  uint32_t pw0, pw1, pw2;
-  uint32_t pn;              // bytes of the pending piece | bit shift of its first byte << 8; 0 = none
-  // match being copied: bytes still to be issued after the pending piece, and the distance to copy from
-  // (a multiple of the match distance, doubled per piece while it is shorter than a piece)
-  uint32_t cp_rem, cp_d;
+  uint32_t q, q0, qend;
+  uint64_t acc_lo, acc_hi;  // bytes of the current 16-byte chunk decided so far
+  // match bitmap of this block
+  uint32_t* bitmap;
+  uint32_t bm, bm_w;
   // canonical-code limits: llim[i] = lim[2i] | lim[2i+1] << 16, lim[0] = 0x8000 (never reached)
   uint32_t llim[8], dlim[8];
   uint8_t* slab;            // shared memory (host model: heap)
+#if NGSQ_DEC_VARIANT & 1
   const uint32_t* lut;      // base_lut_entry(0..63)
+#endif
   uint32_t err;
   int state;
   bool bfinal;
@@ -215,13 +260,28 @@ struct Lane {
   NGSQ_HD bool overran() const { return byte_ptr() > in_end + 8; }
 
   // ---------------- output ----------------
-  static NGSQ_HD void store16_if(bool c, uint8_t* p, uint64_t lo, uint64_t hi) {  // device: one @p ST.128; host: an if
+  // Decided bytes are gathered into an aligned 16-byte chunk {acc_lo, acc_hi} and stored with one
+  // 128-bit store; bytes of the chunk that belong to a match are stored as zero and overwritten by
+  // the resolve kernel afterwards.  (Measured alternative: a 32-bit word accumulator needs 7 % fewer
+  // instructions but its partial-sector stores raise the kernel's DRAM traffic from 1.3x to 1.6x of
+  // C + D; the run time is the same.)
+  NGSQ_HD void flush_chunk(uint32_t cq) {  // cq: multiple of 16; the chunk covers coordinates [cq, cq+16)
+    if (cq >= q0 && cq + 16 <= qend) {
 #if defined(__CUDA_ARCH__)
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %0, 0;\n\tcvta.to.global.u64 a, %1;\n\t@p st.global.v4.u32 [a], {%2, %3, %4, %5};\n\t}"
-                 :: "r"((uint32_t)c), "l"(p), "r"((uint32_t)lo), "r"((uint32_t)(lo >> 32)), "r"((uint32_t)hi), "r"((uint32_t)(hi >> 32)) : "memory");
+      *reinterpret_cast<uint4*>(obase + cq) = make_uint4((uint32_t)acc_lo, (uint32_t)(acc_lo >> 32), (uint32_t)acc_hi, (uint32_t)(acc_hi >> 32));
 #else
-    if (c) { memcpy(p, &lo, 8); memcpy(p + 8, &hi, 8); }
+      memcpy(obase + cq, &acc_lo, 8);
+      memcpy(obase + cq + 8, &acc_hi, 8);
 #endif
+#ifdef NGSQ_HOST_MODEL
+      if (ctr) ctr->chunk_stores++;
+#endif
+    } else {
+      flush_edge(obase, q0, qend, acc_lo, acc_hi, cq);
+#ifdef NGSQ_HOST_MODEL
+      if (ctr) ctr->edge_stores++;
+#endif
+    }
   }
   // first / last chunk of the block shares its 16 bytes with the neighbouring block: bytes only
   // (static and by value: a non-inlined member call would force the whole Lane into local memory)
@@ -232,9 +292,61 @@ struct Lane {
       if (c >= q0 && c < qend) obase[c] = (uint8_t)((i < 8 ? lo >> (8 * i) : hi >> (8 * (i - 8))));
     }
   }
-  // stores the chunk [cq, cq + 16) as it stands in the accumulator (bytes not produced yet: zeros; they are this
-  // lane's to overwrite) when c holds
-  NGSQ_HD void store_chunk_if(bool c, uint32_t cq) {
+  // append the low n (1..3) bytes of v, then leave `sk` bytes to the resolve kernel
+  NGSQ_HD void emit(uint32_t v, uint32_t n, uint32_t sk) {
+    const uint32_t pos = q & 15;
+    const uint32_t s = pos * 8;
+    // 128-bit left shift of a 24-bit value by s in [0, 120], without shift counts >= 64
+    const uint64_t V = v;
+    const bool in_lo = s < 64;
+    const uint32_t s6 = s & 63;
+    const uint64_t up = V << s6;                 // s < 64: low half;  s >= 64: high half
+    const uint64_t carry = (V >> 1) >> (63 - s6);  // s < 64: bits that cross into the high half
+    acc_lo |= in_lo ? up : 0;
+    acc_hi |= in_lo ? carry : up;
+    const uint32_t nq = q + n;
+    if ((nq ^ q) & 16) {  // chunk complete (possibly with bytes spilling into the next one)
+      flush_chunk(q & ~15u);
+      acc_lo = (pos + n > 16) ? (uint64_t)(v >> (8 * (16 - pos))) : 0;
+      acc_hi = 0;
+    }
+    q = nq;
+    if (sk) {
+      const uint32_t sq = q + sk;
+      if ((sq >> 4) != (q >> 4)) {
+        if (q & 15) flush_chunk(q & ~15u);
+        acc_lo = 0;
+        acc_hi = 0;
+      }
+      q = sq;
+    }
+  }
+  NGSQ_HD void mark_match(uint32_t p) {  // p: block-relative position of the match start
+    uint32_t w = p >> 5;
+    if (w != bm_w) {
+      if (bm) bitmap[bm_w] = bm;
+      bm_w = w;
+      bm = 0;
+    }
+    bm |= 1u << (p & 31);
+  }
+  // ---- variants 2 / 4: stores under a predicate instead of a branch (device: one @p ST; host: an if) ----
+  static NGSQ_HD void store16_if(bool c, uint8_t* p, uint64_t lo, uint64_t hi) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %0, 0;\n\tcvta.to.global.u64 a, %1;\n\t@p st.global.v4.u32 [a], {%2, %3, %4, %5};\n\t}"
+                 :: "r"((uint32_t)c), "l"(p), "r"((uint32_t)lo), "r"((uint32_t)(lo >> 32)), "r"((uint32_t)hi), "r"((uint32_t)(hi >> 32)) : "memory");
+#else
+    if (c) { memcpy(p, &lo, 8); memcpy(p + 8, &hi, 8); }
+#endif
+  }
+  static NGSQ_HD void store4_if(bool c, uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %0, 0;\n\tcvta.to.global.u64 a, %1;\n\t@p st.global.u32 [a], %2;\n\t}" :: "r"((uint32_t)c), "l"(p), "r"(v) : "memory");
+#else
+    if (c) *p = v;
+#endif
+  }
+  NGSQ_HD void flush_chunk_if(bool c, uint32_t cq) {
     const bool inner = cq >= q0 && cq + 16 <= qend;
     store16_if(c && inner, obase + cq, acc_lo, acc_hi);
     if (c && !inner) flush_edge(obase, q0, qend, acc_lo, acc_hi, cq);  // first / last chunk of the block only
@@ -242,69 +354,48 @@ struct Lane {
     if (ctr && c) { if (inner) ctr->chunk_stores++; else ctr->edge_stores++; }
 #endif
   }
-  // appends the low n (1..8) bytes of hi:lo at q; a completed chunk leaves as one 128-bit store
-  NGSQ_HD void append(uint32_t lo, uint32_t hi, uint32_t n) {
-    const uint32_t p = q & 15;
-    uint64_t V = (uint64_t)lo | ((uint64_t)hi << 32);
-    V = n >= 8 ? V : V & ((1ull << ((8 * n) & 63)) - 1ull);  // loads carry bytes beyond the piece
-    // 192-bit left shift of V by 8p bits, without shift counts >= 64: A -> acc_lo, B -> acc_hi, C -> the next chunk
-    const bool in_lo = p < 8;
-    const uint32_t s6 = (8 * p) & 63;
+  NGSQ_HD void emit_sel(uint32_t v, uint32_t n, uint32_t sk) {  // same contract as emit()
+    const uint32_t pos = q & 15;
+    const uint32_t s = pos * 8;
+    const uint64_t V = v;
+    const bool in_lo = s < 64;
+    const uint32_t s6 = s & 63;
     const uint64_t up = V << s6;
-    const uint64_t carry = (V >> 1) >> (63 - s6);  // the bits that leave `up` at the top
+    const uint64_t carry = (V >> 1) >> (63 - s6);
     acc_lo |= in_lo ? up : 0;
     acc_hi |= in_lo ? carry : up;
-    const uint64_t C = in_lo ? 0 : carry;
     const uint32_t nq = q + n;
-    const bool full = ((nq ^ q) & 16) != 0;  // the piece completes this chunk (n <= 8 < 16: at most one)
-    store_chunk_if(full, q & ~15u);
-    acc_lo = full ? C : acc_lo;
-    acc_hi = full ? 0 : acc_hi;
-    q = nq;
+    const bool cross1 = ((nq ^ q) & 16) != 0;  // the token completes this chunk
+    flush_chunk_if(cross1, q & ~15u);
+    // bytes of the token that spill into the next chunk: 16 - pos is 1..3 whenever cross1 holds (n <= 3),
+    // and the shifted-out value is 0 when the token ends exactly at the boundary
+    const uint32_t left = v >> ((8 * (16 - pos)) & 31);
+    acc_lo = cross1 ? (uint64_t)left : acc_lo;
+    acc_hi = cross1 ? 0 : acc_hi;
+    const uint32_t sq = nq + sk;
+    const bool cross2 = (sq >> 4) != (nq >> 4);  // the match bytes left to the resolve kernel leave the chunk
+    flush_chunk_if(cross2 && (nq & 15), nq & ~15u);
+    acc_lo = cross2 ? 0 : acc_lo;
+    acc_hi = cross2 ? 0 : acc_hi;
+    q = sq;
+  }
+  NGSQ_HD void mark_match_if(bool ok, uint32_t p) {
+    const uint32_t w = p >> 5;
+    const bool nw = ok && w != bm_w;
+    store4_if(nw && bm != 0, bitmap + bm_w, bm);
+    bm = nw ? 0 : bm;
+    bm_w = nw ? w : bm_w;
+    bm |= ok ? 1u << (p & 31) : 0u;
   }
   NGSQ_HD void finish_output() {
-    store_chunk_if((q & 15) != 0, q & ~15u);
+    if (q & 15) flush_chunk(q & ~15u);
     acc_lo = 0;
     acc_hi = 0;
+    if (bm) bitmap[bm_w] = bm;
+    bm = 0;
   }
 
-  // ---------------- match copy ----------------
-  // The pending piece joins the output: its words have had one iteration to arrive.
-  NGSQ_HD void append_pending() {
-    const uint32_t n = pn & 255u, sh = pn >> 8;
-    if (n) append(funnel_r(pw0, pw1, sh), funnel_r(pw1, pw2, sh), n);
-    pn = 0;
-  }
-  // Issues the loads of the next piece of the match being copied (cp_rem > 0, nothing pending).
-  NGSQ_HD void issue_piece() {
-    uint32_t n = cp_rem < kPieceBytes ? cp_rem : kPieceBytes;
-    n = cp_d < n ? cp_d : n;  // never read what this piece itself writes
-    const uint32_t src = q - cp_d;  // aligned coordinates
-    // the source reaches into the open chunk: put the chunk's bytes where the load finds them
-    store_chunk_if(src + n > (q & ~15u) && (q & 15) != 0, q & ~15u);
-#ifdef NGSQ_HOST_MODEL
-    if (ctr) { ctr->pieces++; if (src + n > (q & ~15u) && (q & 15) != 0) ctr->open_chunk_stores++; }
-#endif
-    const uint8_t* s = obase + src;
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3);
-    const uint32_t* a = reinterpret_cast<const uint32_t*>(s - mis);
-#if defined(__CUDA_ARCH__)
-    pw0 = a[0];
-    pw1 = a[1];
-    pw2 = 0;
-    if (mis + n > 8) pw2 = a[2];
-#else
-    memcpy(&pw0, a, 4);
-    memcpy(&pw1, a + 1, 4);
-    pw2 = 0;
-    if (mis + n > 8) memcpy(&pw2, a + 2, 4);
-#endif
-    pn = n | (mis * 8) << 8;
-    cp_rem -= n;
-    cp_d = cp_d < kPieceBytes ? cp_d << 1 : cp_d;  // the n = cp_d bytes just issued repeat the pattern: the period doubles
-  }
-
-  NGSQ_HD void begin_block(const BlockDesc& d, uint8_t* out) {
+  NGSQ_HD void begin_block(const BlockDesc& d, uint8_t* out, uint32_t* bitmap_of_block) {
     uint8_t* o = out + d.out_off;
     uint32_t ab = (uint32_t)(reinterpret_cast<uintptr_t>(o) & 15);
     obase = o - ab;
@@ -313,10 +404,9 @@ struct Lane {
     qend = ab + d.isize;
     acc_lo = 0;
     acc_hi = 0;
-    pn = 0;
-    pw0 = pw1 = pw2 = 0;
-    cp_rem = 0;
-    cp_d = 0;
+    bitmap = bitmap_of_block;
+    bm = 0;
+    bm_w = 0;
     err = 0;
     bfinal = false;
     in_end = reinterpret_cast<const uint8_t*>(d.in_off) + d.clen;
@@ -327,8 +417,6 @@ struct Lane {
     if (!e && q != qend) e = kBlkIsize;
     err = e;
     finish_output();
-    pn = 0;
-    cp_rem = 0;
     state = LS_IDLE;
   }
 
@@ -372,7 +460,17 @@ struct Lane {
   // code length of the next symbol: 1 + number of limits the next 15 bits (MSB first) reach
   static NGSQ_HD uint32_t code_len(uint32_t x, const uint32_t* lim_packed) {
     const uint32_t x2 = (x * 0x10001u) | 0x80008000u;
-#if defined(__CUDA_ARCH__)
+#if NGSQ_DEC_VARIANT & 16
+    // bytes 1 and 3 of (x2 - lim) carry the "x >= lim" flags in their top bits: replicate them to 0x00 / 0xFF
+    // (= 0 / -1 as signed bytes) and add the sixteen of them up with four dot products
+    const uint32_t h0 = byte_perm(x2 - lim_packed[0], x2 - lim_packed[1], 0xFDB9);
+    const uint32_t h1 = byte_perm(x2 - lim_packed[2], x2 - lim_packed[3], 0xFDB9);
+    const uint32_t h2 = byte_perm(x2 - lim_packed[4], x2 - lim_packed[5], 0xFDB9);
+    const uint32_t h3 = byte_perm(x2 - lim_packed[6], x2 - lim_packed[7], 0xFDB9);
+    const int c01 = dp4a_s8(h1, 0x01010101u, dp4a_s8(h0, 0x01010101u, -1));  // -1 - (limits 0..7 reached)
+    const int c23 = dp4a_s8(h3, 0x01010101u, dp4a_s8(h2, 0x01010101u, 0));   // -(limits 8..15 reached)
+    return (uint32_t)(0 - c01 - c23);
+#elif defined(__CUDA_ARCH__)
     // bit 15 of each half of (x2 - lim) says x >= lim: gather the 16 flag bytes with four byte
     // permutes, interleave their top bits into one word, popcount
     const uint32_t g0 = __byte_perm(x2 - lim_packed[0], x2 - lim_packed[1], 0x7531);
@@ -413,7 +511,7 @@ struct Lane {
       if ((v ^ nv) != 0xFFFFu) { end_block(kBlkBadStream); return; }
       const uint8_t* sp = byte_ptr();
       if (q + v > qend || sp + v > in_end) { end_block(kBlkOverrun); return; }
-      for (uint32_t k = 0; k < v; ++k) append(sp[k], 0, 1);
+      for (uint32_t k = 0; k < v; ++k) emit(sp[k], 1, 0);
       br_init(sp + v);
       if (bfinal) end_block(0);
       return;  // state stays LS_HEADER otherwise
@@ -509,25 +607,22 @@ struct Lane {
     state = LS_DECODE;
   }
 
-  // ---------------- one loop iteration: append the pending piece, then one symbol or one more piece ----------------
+  // ---------------- one literal/length(+distance) symbol ----------------
   // Straight-line on purpose: every warp step runs the union of the paths its lanes take and waits
-  // out every branch, so range checks only accumulate flags that are tested once at the end, and the
-  // length / distance bases come from a table.  Out-of-range values are clamped where they index memory;
-  // a flagged block is failed before any of its bytes is read back.
+  // out every branch (ncu: each warp is bound by its own dependency / branch-resolve latency, not by
+  // issue slots), so range checks only accumulate flags that are tested once at the end, and the
+  // length / distance bases are computed without branches.  Out-of-range values are clamped where
+  // they index memory; a flagged block is failed and never reaches the resolve kernel.
   NGSQ_HD void step() {
-    append_pending();
-    if (cp_rem) {  // this lane is still copying a long (or overlapping) match: one more piece, no symbol
-#ifdef NGSQ_HOST_MODEL
-      if (ctr) ctr->copy_iterations++;
-#endif
-      issue_piece();
-      return;
-    }
     refill();
     const uint32_t x = brev32(peek()) >> 17;
     const uint32_t len = code_len(x, llim);             // 1..15, 16 = bits beyond an incomplete code
     uint32_t bad_stream = len >> 4, overrun = 0;
+#if NGSQ_DEC_VARIANT & 8
     const uint32_t bt = ll_bt()[len];  // 1..16
+#else
+    const uint32_t bt = ll_bt()[len & 15];
+#endif
     const uint32_t idx = ((x >> ((15 - len) & 31)) + bt) & 0xFFFFu;  // index into sorted (the base is kept mod 2^16)
     const uint32_t s8 = ll_sorted()[idx < 288 ? idx : 0];
     const bool upper = idx >= (bt >> 16);  // symbol >= 256
@@ -535,6 +630,7 @@ struct Lane {
 #ifdef NGSQ_HOST_MODEL
     if (ctr) { ctr->symbols++; ctr->ll_len_hist[len]++; }
 #endif
+    uint32_t v = s8, n = 1, sk = 0;
     if (upper) {
       if (s8 == 0 && !bad_stream) {  // end of block
         if (overran()) { end_block(kBlkBadStream); return; }
@@ -544,12 +640,26 @@ struct Lane {
       // length symbol 257 + li: li < 8: 3 + li;  li = 28: 258;  else 3 + ((4 + (li & 3)) << eb) + extra, eb = (li - 4) >> 2
       const uint32_t li = s8 - 1;
       bad_stream |= li > 28;
+#if NGSQ_DEC_VARIANT & 1
       const uint32_t le = lut[li & 31];
       const uint32_t mlen = 3 + (le & 255) + take(le >> 8);
+#else
+      const uint32_t lc = li > 28 ? 28 : li;
+      uint32_t eb = ((lc < 4 ? 4 : lc) - 4) >> 2;
+      uint32_t lbase = (4 + (lc & 3)) << eb;
+      lbase = lc < 4 ? lc : lbase;
+      lbase = lc == 28 ? 255 : lbase;
+      eb = lc == 28 ? 0 : eb;
+      const uint32_t mlen = 3 + lbase + take(eb);
+#endif
       const uint32_t dx = brev32(peek()) >> 17;
       const uint32_t dl = code_len(dx, dlim);
       bad_stream |= dl >> 4;
+#if NGSQ_DEC_VARIANT & 8
       const uint32_t di = ((dx >> ((15 - dl) & 31)) + (uint32_t)d_base()[dl]) & 31u;
+#else
+      const uint32_t di = ((dx >> ((15 - dl) & 31)) + (uint32_t)(int)d_base()[dl & 15]) & 31u;
+#endif
       const uint32_t ds = d_sorted()[di];
       bad_stream |= ds > 29;
       drop(dl);
@@ -557,27 +667,41 @@ struct Lane {
       if (ctr) ctr->d_len_hist[dl]++;
 #endif
       // distance symbol ds: ds < 4: 1 + ds;  else 1 + ((2 + (ds & 1)) << deb) + extra, deb = (ds >> 1) - 1
+#if NGSQ_DEC_VARIANT & 1
       const uint32_t de = lut[32 + (ds & 31)];
       const uint32_t dist = 1 + (de & 0xFFFFu) + take(de >> 16);
-      overrun |= (dist > q - q0) | (q + mlen > qend);
-      if (bad_stream | overrun) { end_block(bad_stream ? kBlkBadStream : kBlkOverrun); return; }
-#ifdef NGSQ_HOST_MODEL
-      if (ctr) { ctr->matches++; ctr->match_bytes += mlen; ctr->match_len_hist[mlen]++; }
+#else
+      const uint32_t dc = ds > 29 ? 29 : ds;
+      const uint32_t deb = ((dc >> 1) < 1 ? 1 : (dc >> 1)) - 1;
+      uint32_t dbase = 1 + ((2 + (dc & 1)) << deb);
+      dbase = dc < 2 ? dc + 1 : dbase;
+      const uint32_t dist = dbase + take(deb);
 #endif
-      cp_rem = mlen;
-      cp_d = dist;
-      issue_piece();
+      const uint32_t p = q - q0;
+      overrun |= (dist > p) | (q + mlen > qend);
+#if NGSQ_DEC_VARIANT & 2
+      mark_match_if(!(bad_stream | overrun), p);
+#else
+      if (!(bad_stream | overrun)) mark_match(p);
+#endif
+      v = (mlen - 3) | ((dist - 1) << 8);
+      n = 3;
+      sk = mlen - 3;
+#ifdef NGSQ_HOST_MODEL
+      if (ctr) { ctr->matches++; ctr->match_bytes += mlen; }
+#endif
     } else {
       overrun |= q >= qend;
-      if (bad_stream | overrun) { end_block(bad_stream ? kBlkBadStream : kBlkOverrun); return; }
 #ifdef NGSQ_HOST_MODEL
       if (ctr) ctr->literals++;
 #endif
-      pw0 = s8;  // a literal is a piece whose byte is known at once
-      pw1 = 0;
-      pw2 = 0;
-      pn = 1;
     }
+    if (bad_stream | overrun) { end_block(bad_stream ? kBlkBadStream : kBlkOverrun); return; }
+#if NGSQ_DEC_VARIANT & 4
+    emit_sel(v, n, sk);
+#else
+    emit(v, n, sk);
+#endif
   }
 };
 
