@@ -165,6 +165,7 @@ cov_resolve_kernel(const int32_t* __restrict__ diff, uint32_t n, const int64_t* 
     int64_t depth = tile_base[t] + wbase + x - tsum;
     // positions -> depth; run-length aggregated histogram; bin sums
     const uint32_t k0 = (t * kCovTile + kCovBin - 1) / kCovBin;  // bin of the tile's first position (0 for position 0)
+    const uint32_t bin_last = k0 * kCovBin;                       // last position of that bin: bin k = (50000(k-1), 50000k]
     unsigned long long s0 = 0, s1 = 0;
     int64_t run_d = -1;
     uint32_t run_n = 0;
@@ -173,8 +174,7 @@ cov_resolve_kernel(const int32_t* __restrict__ diff, uint32_t n, const int64_t* 
       uint32_t i = p0 + k;
       depth += v[k];
       if (i < n) {
-        uint32_t bin = (i + kCovBin - 1) / kCovBin;
-        if (bin == k0) s0 += (unsigned long long)depth; else s1 += (unsigned long long)depth;
+        if (i <= bin_last) s0 += (unsigned long long)depth; else s1 += (unsigned long long)depth;  // a tile meets at most two bins
         if (depth == run_d) ++run_n;
         else {
           if (run_n) atomicAdd(&hist[cov_hist_slot(run_d)], run_n);

@@ -1,9 +1,11 @@
 // CRC32 (IEEE 802.3, reflected, as in gzip) of every inflated BGZF block, compared with the
 // block trailer — the check noodles-bgzf performs on each block it reads.
-// One warp per block.  Every lane owns a contiguous slice of the block and runs FOUR independent
-// table CRCs over its quarters: the byte-table lookup chain (load -> xor -> shared-memory lookup) is
-// latency bound, and one chain per lane left the kernel at 1.5 TB/s with 12.5 + 9 stall cycles per
-// issue on the shared-memory and global scoreboards (ncu, profiles/round1_v2_kernels_ncu.md).  The
+// One warp per block.  Every lane owns a contiguous slice of the block and runs TWO independent
+// table CRCs over its halves, 64 bytes of each per loop iteration: the byte-table lookup chain (load -> xor ->
+// shared-memory lookup) is latency bound, and one chain per lane left the kernel at 1.5 TB/s with 12.5 + 9 stall cycles
+// per issue on the shared-memory and global scoreboards (ncu, profiles/round1_v2_kernels_ncu.md).  Four chains per lane
+// were measured too: 0.9 M concurrent streams x 128-byte lines no longer fit the L2 and every line came from DRAM twice
+// (profiles/round2_crc_variants.md).  The
 // partial CRCs are merged with CRC(A||B) = CRC(A) * x^(8|B|) mod P xor CRC(B), a carry-less multiply
 // modulo the CRC polynomial; the factors x^(8k) mod P for every k <= 65536 come from a 256 KB table
 // (L2-resident) instead of a square-and-multiply chain per lane.
@@ -55,7 +57,8 @@ inline void crc_make_tables(CrcTables& t) {
 // i * 32 + l, i.e. always in bank l) so the 32 data-dependent lookups of a warp never conflict, and
 // every lane streams its quarters with 128-bit loads.
 constexpr int kCrcThreads = 256;
-constexpr int kCrcStreams = 4;
+constexpr int kCrcStreams = 2;
+constexpr int kCrcStep = 64;  // bytes of a stream per loop iteration: half a 128-byte line, whole sectors
 constexpr size_t kCrcSmem = 256 * 32 * 4;
 
 __global__ void __launch_bounds__(kCrcThreads)
@@ -74,8 +77,8 @@ crc32_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ bloc
     const BlockDesc d = blocks[b];
     const uint8_t* p = out + d.out_off;
     const uint32_t n = d.isize;
-    // lane slice [lo, hi): `per` bytes, a multiple of 128; quarter j = [lo + j*q, lo + (j+1)*q) clipped to n.
-    // All quarter starts are multiples of 32 bytes into the block, so every stream has the block's alignment and
+    // lane slice [lo, hi): `per` bytes, a multiple of 128; part j = [lo + j*q, lo + (j+1)*q) clipped to n.
+    // All part starts are multiples of 64 bytes into the block, so every stream has the block's alignment and
     // consumes whole 32-byte sectors: a lane's loads share no sector with any other lane's, and with 16-byte steps the
     // second half of every sector had left the (small) L1 before it was asked for — 4.6x DRAM traffic (ncu, profiles/).
     const uint32_t per = ((n + 31) / 32 + 127) & ~127u;
@@ -95,23 +98,24 @@ crc32_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ bloc
       for (int j = 0; j < kCrcStreams; ++j)
         if (s_lo[j] + t < s_hi[j]) NGSQ_CRC_BYTE(c[j], p[s_lo[j] + t]);
     }
-    // whole sectors, the four streams in lock step (stream 0 is never shorter than the others)
+    // whole sectors, the streams in lock step (stream 0 is never shorter than the others)
     uint32_t k_n[kCrcStreams];
 #pragma unroll
-    for (int j = 0; j < kCrcStreams; ++j) k_n[j] = s_lo[j] + head < s_hi[j] ? (s_hi[j] - s_lo[j] - head) >> 5 : 0u;
+    for (int j = 0; j < kCrcStreams; ++j) k_n[j] = s_lo[j] + head < s_hi[j] ? (s_hi[j] - s_lo[j] - head) / kCrcStep : 0u;
     for (uint32_t k = 0; k < k_n[0]; ++k) {
-      uint4 v[kCrcStreams][2];
+      uint4 v[kCrcStreams][kCrcStep / 16];
 #pragma unroll
       for (int j = 0; j < kCrcStreams; ++j) {
-        v[j][0] = v[j][1] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int t = 0; t < kCrcStep / 16; ++t) v[j][t] = make_uint4(0, 0, 0, 0);
         if (k < k_n[j]) {
-          const uint4* src = reinterpret_cast<const uint4*>(p + s_lo[j] + head + 32 * k);
-          v[j][0] = src[0];
-          v[j][1] = src[1];
+          const uint4* src = reinterpret_cast<const uint4*>(p + s_lo[j] + head + kCrcStep * k);
+#pragma unroll
+          for (int t = 0; t < kCrcStep / 16; ++t) v[j][t] = src[t];
         }
       }
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
+      for (int w = 0; w < kCrcStep / 4; ++w) {
 #pragma unroll
         for (int sh = 0; sh < 32; sh += 8) {
 #pragma unroll
@@ -126,7 +130,7 @@ crc32_kernel(const uint8_t* __restrict__ out, const BlockDesc* __restrict__ bloc
     // tail bytes of each stream
 #pragma unroll
     for (int j = 0; j < kCrcStreams; ++j)
-      for (uint32_t i = s_lo[j] + head + 32 * k_n[j]; i < s_hi[j]; ++i) NGSQ_CRC_BYTE(c[j], p[i]);
+      for (uint32_t i = s_lo[j] + head + kCrcStep * k_n[j]; i < s_hi[j]; ++i) NGSQ_CRC_BYTE(c[j], p[i]);
     // merge the lane's quarters (Horner), then shift the lane's CRC by the bytes that follow its slice
     uint32_t h = 0;
 #pragma unroll

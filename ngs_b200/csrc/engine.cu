@@ -453,7 +453,7 @@ int ensure_wave_buffers(ngsq_engine* e, int s, uint32_t n, uint64_t bytes) {
     size_t want = bytes + bytes / 8;
     const uint64_t full = (uint64_t)launch_quantum(e) * 65536;
     if (e->cfg.reserve_inflated) want = (size_t)std::max<uint64_t>(bytes, std::min<uint64_t>(e->cfg.reserve_inflated, full));
-    if ((rc = fresh(e, e->d_slot[s], (size_t)e->headroom + want + 64, "inflated slot"))) return rc;
+    if ((rc = fresh(e, e->d_slot[s], (size_t)e->headroom + want + 512, "inflated slot"))) return rc;
     e->slot_cap[s] = want;
   }
   if (n > e->scan_cap) {

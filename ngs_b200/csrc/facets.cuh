@@ -126,29 +126,49 @@ constexpr uint32_t kQualPre = 5;  // quality positions per lane loaded one recor
 // Fixed: the engine streams the file and cannot know the longest read when it launches the first wave.
 constexpr uint32_t kQualSmemPositions = 152;
 
-// loads of one record that phase B needs: quality bytes at positions lane + 32k (0x100 where the
-// string or the shared-memory table ends) and, for lanes < 25 of a GC-eligible record, the three
-// sequence bytes holding bases gj + 4*lane .. +3 at either nibble phase (the third byte may lie just
-// past the window: still inside the record, the qualities follow the sequence)
-__device__ __forceinline__ void facet_prefetch(const uint8_t* sq, uint32_t ls, uint32_t gj, uint32_t qpos_smem, uint32_t lane,
-                                               uint32_t (&qb)[kQualPre], uint32_t (&gb)[3]) {
-  // nothing here may consume a loaded value (no selects, no shifts): the loads must stay in flight
-  // while the previous record is tallied
+// loads of one record that phase B needs: the quality bytes at positions lane + 32k, k < kQualPre.  Unconditional
+// (bytes behind a short string belong to the next record or to the slot's slack; they are masked when they are
+// tallied): one base address, five immediate offsets, no predicates.  Nothing here may consume a loaded value (no
+// selects, no shifts): the loads must stay in flight while the previous record is tallied.
+__device__ __forceinline__ void facet_prefetch(const uint8_t* sq, uint32_t ls, uint32_t lane, uint32_t (&qb)[kQualPre]) {
   const uint8_t* qlane = sq + (ls + 1) / 2 + lane;
-  const uint32_t n_s = ls < qpos_smem ? ls : qpos_smem;
-  const uint32_t n_k = n_s > lane ? (n_s - lane + 31) >> 5 : 0;  // positions lane + 32k < n_s  <=>  k < n_k
 #pragma unroll
-  for (uint32_t k = 0; k < kQualPre; ++k) {
-    qb[k] = 0x100u;
-    if (k < n_k) qb[k] = __ldg(qlane + 32 * k);
+  for (uint32_t k = 0; k < kQualPre; ++k) qb[k] = __ldg(qlane + 32 * k);
+}
+
+// G/C and A/T bases among the 100 bases that start at base `gj` of a 4-bit packed sequence (gc_content.rs:76-100), by the
+// record's own lane: 13 unaligned words over the window's whole bytes (49 or 50), the two odd nibbles at its ends.
+// A, C, G, T are the one-hot codes 1, 2, 4, 8: per nibble, C|G <=> exactly one of bits 1, 2 and neither of bits 0, 3;
+// A|T <=> exactly one of bits 0, 3 and neither of bits 1, 2 (eight nibbles of a word at once).
+__device__ __forceinline__ void gc_window_counts(const uint8_t* seq, uint32_t gj, uint32_t* gc_out, uint32_t* at_out) {
+  const uint32_t odd = gj & 1u;
+  const uint8_t* fp = seq + ((gj + 1) >> 1);  // first whole byte of the window
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(fp) & ~uintptr_t(3));
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(fp) & 3) * 8;
+  uint32_t gc = 0, at = 0, g_acc = 0, a_acc = 0;
+  uint32_t prev = __ldg(w);
+#pragma unroll
+  for (int i = 0; i < 13; ++i) {
+    const uint32_t nxt = __ldg(w + i + 1);
+    uint32_t u = __funnelshift_r(prev, nxt, sh);
+    prev = nxt;
+    if (i == 12) u &= odd ? 0xFFu : 0xFFFFu;  // bytes 48 (and 49): 49 whole bytes when the window starts on a low nibble
+    const uint32_t b1 = u >> 1, b2 = u >> 2, b3 = u >> 3;
+    g_acc |= ((b1 ^ b2) & ~(u | b3) & 0x11111111u) << (i & 3);
+    a_acc |= ((u ^ b3) & ~(b1 | b2) & 0x11111111u) << (i & 3);
+    if ((i & 3) == 3 || i == 12) {
+      gc += __popc(g_acc);
+      at += __popc(a_acc);
+      g_acc = a_acc = 0;
+    }
   }
-  gb[0] = gb[1] = gb[2] = 0;
-  if (gj != 0xFFFFFFFFu && lane < 25) {
-    const uint8_t* bp = sq + ((gj + 4 * lane) >> 1);
-    gb[0] = __ldg(bp);
-    gb[1] = __ldg(bp + 1);
-    gb[2] = __ldg(bp + 2);
+  if (odd) {  // first base: low nibble of the byte before; last base: high nibble of the byte behind the whole bytes
+    const uint32_t n1 = __ldg(seq + (gj >> 1)) & 15u, n2 = (uint32_t)__ldg(seq + ((gj + 99) >> 1)) >> 4;
+    gc += (n1 == 2u || n1 == 4u) + (n2 == 2u || n2 == 4u);
+    at += (n1 == 1u || n1 == 8u) + (n2 == 1u || n2 == 8u);
   }
+  *gc_out = gc;
+  *at_out = at;
 }
 
 __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
@@ -171,7 +191,7 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
   const uint64_t n_warps = (uint64_t)gridDim.x * warps_per_cta;
   const bool do_rec = P.flags & 1u;
   uint32_t acc = 0;                        // lane k owns counter k (bit k of every record's `bits`)
-  uint32_t sum_gc = 0, sum_at = 0, sum_oth = 0;  // warp-uniform
+  uint32_t sum_gc = 0, sum_at = 0, sum_oth = 0;  // per lane (the record's own lane counts its GC window)
   uint32_t err_qual = 0, err_rec = 0, max_qpos = 0, qual_over = 0;
   const uint64_t n_rec = P.st->fatal ? 0 : P.st->wave_rec, rec_base = P.st->rec_base;
   const bool do_cov = (P.flags & 2u) && P.cov_scatter;
@@ -332,59 +352,47 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
       const uint32_t m = __ballot_sync(0xFFFFFFFFu, (bits >> k) & 1u);
       if ((int)lane == k) acc += __popc(m);
     }
+    // ---- GC window (gc_content.rs:76-100): the record's own lane counts its 100 bases
+    if (gc_on) {
+      uint32_t gc, at;
+      gc_window_counts(seq, gc_off, &gc, &at);
+      sum_gc += gc; sum_at += at; sum_oth += 100 - gc - at;
+      atomicAdd(&s_gc[gc], 1u);  // round(gc / 100 * 100) == gc
+    }
 
     // ================= phase B: one record per warp step =================
-    // Software-pipelined: the bytes of the NEXT record (first 160 quality positions, the three
-    // sequence bytes of this lane's part of the GC window) are loaded before the current record is
-    // tallied, so a warp always has one record's worth of loads in flight.
+    // Quality by position.  Software-pipelined: the first 160 quality positions of the NEXT record are loaded before
+    // the current one is tallied, so a warp always has one record's worth of loads in flight.
     uint32_t todo = __ballot_sync(0xFFFFFFFFu, rec_on && lseq != 0);
     const uint8_t* sq = nullptr;   // current record
-    uint32_t ls = 0, gj = 0xFFFFFFFFu;
-    uint32_t qb[kQualPre], gb[3];  // prefetched: quality bytes (0x100 = beyond the string), GC window bytes
+    uint32_t ls = 0;
+    uint32_t qb[kQualPre];         // prefetched quality bytes of positions lane + 32k (unmasked)
     {
       const int j = todo ? __ffs(todo) - 1 : 0;
       sq = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)seq, j));
       ls = __shfl_sync(0xFFFFFFFFu, lseq, j);
-      gj = __shfl_sync(0xFFFFFFFFu, gc_on ? gc_off : 0xFFFFFFFFu, j);
-      if (todo) facet_prefetch(sq, ls, gj, P.qpos_smem, lane, qb, gb);
+      if (todo) facet_prefetch(sq, ls, lane, qb);
     }
+    const uint32_t n_pre = P.qpos_smem < 32 * kQualPre ? P.qpos_smem : 32 * kQualPre;  // positions the prefetch covers
+#pragma unroll 2
     while (todo) {
       todo &= todo - 1;
       // ---- issue the next record's loads
       const int jn = todo ? __ffs(todo) - 1 : 0;
       const uint8_t* sq_n = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)seq, jn));
       const uint32_t ls_n = __shfl_sync(0xFFFFFFFFu, lseq, jn);
-      const uint32_t gj_n = __shfl_sync(0xFFFFFFFFu, gc_on ? gc_off : 0xFFFFFFFFu, jn);
-      uint32_t qb_n[kQualPre], gb_n[3];
-      if (todo) facet_prefetch(sq_n, ls_n, gj_n, P.qpos_smem, lane, qb_n, gb_n);
-      const uint8_t* ql = sq + (ls + 1) / 2;
-      // ---- GC window (gc_content.rs:76-100): 100 bases from the record's offset, four per lane
-      if (gj != 0xFFFFFFFFu) {
-        uint32_t gc = 0, at = 0;
-        if (lane < 25) {
-          const uint32_t k0 = gj + 4 * lane;
-          const uint32_t v = (gb[0] << 16) | (gb[1] << 8) | gb[2];
-          const uint32_t u = (v >> ((k0 & 1) ? 4 : 8)) & 0xFFFFu;  // first base in the top nibble
-          // A, C, G, T are the one-hot codes 1, 2, 4, 8: per nibble, C|G <=> exactly one of bits 1, 2 and
-          // neither of bits 0, 3; A|T <=> exactly one of bits 0, 3 and neither of bits 1, 2 (all four nibbles at once)
-          const uint32_t b1 = u >> 1, b2 = u >> 2, b3 = u >> 3;
-          gc = __popc((b1 ^ b2) & ~(u | b3) & 0x1111u);
-          at = __popc((u ^ b3) & ~(b1 | b2) & 0x1111u);
-        }
-        gc = __reduce_add_sync(0xFFFFFFFFu, gc);
-        at = __reduce_add_sync(0xFFFFFFFFu, at);
-        sum_gc += gc; sum_at += at; sum_oth += 100 - gc - at;
-        if (lane == 0) atomicAdd(&s_gc[gc], 1u);  // round(gc/100*100) == gc
-      }
+      uint32_t qb_n[kQualPre];
+      if (todo) facet_prefetch(sq_n, ls_n, lane, qb_n);
       // ---- Quality scores (quality_scores.rs:37-49; presence rule SURVEY App. D.5): one pass.
       // Qualities are present unless every byte is 0xFF; a present string must be <= 93 throughout,
       // so increments for bytes <= 93 are exact whenever the run does not fail.
       // per lane: smallest byte seen (0x100 = none) and largest real byte; "present" <=> some byte != 0xFF,
       // "too big" <=> some byte in 94..255 — two min/max per position instead of compares and branches
+      const uint32_t n_s = ls < n_pre ? ls : n_pre;
       uint32_t q_min = 0x100u, q_max = 0;
 #pragma unroll
       for (uint32_t k = 0; k < kQualPre; ++k) {
-        const uint32_t q = qb[k];
+        const uint32_t q = lane + 32 * k < n_s ? qb[k] : 0x100u;  // beyond the string (or the shared-memory table)
         q_min = min(q_min, q);
         q_max = max(q_max, q & 0xFFu);  // the "beyond the string" marker 0x100 counts as 0 here
         if (q <= 93) {
@@ -393,9 +401,10 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
         }
       }
       bool any_real = q_min < 0xFFu, any_big = q_max > 93;
-      if (ls > (P.qpos_smem < 32 * kQualPre ? P.qpos_smem : 32 * kQualPre)) {  // warp-uniform: short reads never enter
-        const uint32_t n_s = ls < P.qpos_smem ? ls : P.qpos_smem;
-        for (uint32_t i = 32 * kQualPre + lane; i < n_s; i += 32) {  // shared-memory positions beyond the prefetched ones
+      if (ls > n_pre) {  // warp-uniform: short reads never enter
+        const uint8_t* ql = sq + (ls + 1) / 2;
+        const uint32_t n_t = ls < P.qpos_smem ? ls : P.qpos_smem;
+        for (uint32_t i = n_pre + lane; i < n_t; i += 32) {  // shared-memory positions beyond the prefetched ones
           const uint32_t q = __ldg(ql + i);
           any_real |= q != 0xFF;
           if (q > 93) any_big = true;
@@ -418,7 +427,7 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
         if (any_big) err_qual = 1;
         max_qpos = ls > max_qpos ? ls : max_qpos;
       }
-      sq = sq_n; ls = ls_n; gj = gj_n; gb[0] = gb_n[0]; gb[1] = gb_n[1]; gb[2] = gb_n[2];
+      sq = sq_n; ls = ls_n;
 #pragma unroll
       for (uint32_t k = 0; k < kQualPre; ++k) qb[k] = qb_n[k];
     }
@@ -442,6 +451,9 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
       else slot = R_GC_REC + (lane - 18);
       if (lane < 21) atomicAdd((unsigned long long*)&P.res[slot], (unsigned long long)acc);
     }
+    sum_gc = __reduce_add_sync(0xFFFFFFFFu, sum_gc);
+    sum_at = __reduce_add_sync(0xFFFFFFFFu, sum_at);
+    sum_oth = __reduce_add_sync(0xFFFFFFFFu, sum_oth);
     if (lane == 0) {
       if (sum_gc) atomicAdd((unsigned long long*)&P.res[R_GC_NUC + 0], (unsigned long long)sum_gc);
       if (sum_at) atomicAdd((unsigned long long*)&P.res[R_GC_NUC + 1], (unsigned long long)sum_at);
