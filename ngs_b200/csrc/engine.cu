@@ -751,8 +751,9 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->facet_occ, facets_kernel, kFacetThreads, e->facet_smem));
   if (e->facet_occ < 1) e->facet_occ = 1;
   {
-    static const CrcTables* const host_tables = [] { CrcTables* t = new CrcTables; crc_make_tables(*t); return t; }();  // 257 KB, built once per process
-    CUC(cudaMemcpy(e->d_crc_tables, host_tables, sizeof(CrcTables), cudaMemcpyHostToDevice));
+    CrcTables t;
+    crc_make_tables(t);
+    CUC(cudaMemcpy(e->d_crc_tables, &t, sizeof t, cudaMemcpyHostToDevice));
   }
   if (e->cfg.reserve_compressed) {
     // the caller keeps the whole compressed shard on the device (one segment, no recycling needed)

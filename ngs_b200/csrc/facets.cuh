@@ -361,33 +361,27 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
     }
 
     // ================= phase B: one record per warp step =================
-    // Quality by position.  Software-pipelined: the first 160 quality positions of the NEXT record are loaded before
-    // the current one is tallied, so a warp always has one record's worth of loads in flight.
+    // Quality by position.  Software-pipelined two records deep: the first 160 quality positions of the NEXT TWO records
+    // are loaded before the current two are tallied (ncu: with one record in flight per warp the kernel sat on the long
+    // scoreboard at the first use of the prefetched bytes — 14 warps per SM cannot hide an HBM round trip otherwise).
     uint32_t todo = __ballot_sync(0xFFFFFFFFu, rec_on && lseq != 0);
-    const uint8_t* sq = nullptr;   // current record
-    uint32_t ls = 0;
-    uint32_t qb[kQualPre];         // prefetched quality bytes of positions lane + 32k (unmasked)
-    {
-      const int j = todo ? __ffs(todo) - 1 : 0;
+    const uint32_t n_pre = P.qpos_smem < 32 * kQualPre ? P.qpos_smem : 32 * kQualPre;  // positions the prefetch covers
+    // takes the next record off `todo` (warp-uniform) and issues its loads
+    auto fetch = [&](const uint8_t*& sq, uint32_t& ls, uint32_t (&qb)[kQualPre]) -> bool {
+      const bool on = todo != 0;
+      const int j = on ? __ffs(todo) - 1 : 0;
+      todo &= todo - 1;
       sq = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)seq, j));
       ls = __shfl_sync(0xFFFFFFFFu, lseq, j);
-      if (todo) facet_prefetch(sq, ls, lane, qb);
-    }
-    const uint32_t n_pre = P.qpos_smem < 32 * kQualPre ? P.qpos_smem : 32 * kQualPre;  // positions the prefetch covers
-#pragma unroll 2
-    while (todo) {
-      todo &= todo - 1;
-      // ---- issue the next record's loads
-      const int jn = todo ? __ffs(todo) - 1 : 0;
-      const uint8_t* sq_n = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)seq, jn));
-      const uint32_t ls_n = __shfl_sync(0xFFFFFFFFu, lseq, jn);
-      uint32_t qb_n[kQualPre];
-      if (todo) facet_prefetch(sq_n, ls_n, lane, qb_n);
-      // ---- Quality scores (quality_scores.rs:37-49; presence rule SURVEY App. D.5): one pass.
-      // Qualities are present unless every byte is 0xFF; a present string must be <= 93 throughout,
-      // so increments for bytes <= 93 are exact whenever the run does not fail.
-      // per lane: smallest byte seen (0x100 = none) and largest real byte; "present" <=> some byte != 0xFF,
-      // "too big" <=> some byte in 94..255 — two min/max per position instead of compares and branches
+      if (on) facet_prefetch(sq, ls, lane, qb);
+      return on;
+    };
+    // Quality scores of one record (quality_scores.rs:37-49; presence rule SURVEY App. D.5): one pass.
+    // Qualities are present unless every byte is 0xFF; a present string must be <= 93 throughout,
+    // so increments for bytes <= 93 are exact whenever the run does not fail.
+    // per lane: smallest byte seen (0x100 = none) and largest real byte; "present" <=> some byte != 0xFF,
+    // "too big" <=> some byte in 94..255 — two min/max per position instead of compares and branches
+    auto tally = [&](const uint8_t* sq, uint32_t ls, const uint32_t (&qb)[kQualPre]) {
       const uint32_t n_s = ls < n_pre ? ls : n_pre;
       uint32_t q_min = 0x100u, q_max = 0;
 #pragma unroll
@@ -427,9 +421,20 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
         if (any_big) err_qual = 1;
         max_qpos = ls > max_qpos ? ls : max_qpos;
       }
-      sq = sq_n; ls = ls_n;
+    };
+    const uint8_t *sq_a, *sq_b;
+    uint32_t ls_a, ls_b, qb_a[kQualPre], qb_b[kQualPre];
+    bool on_a = fetch(sq_a, ls_a, qb_a), on_b = fetch(sq_b, ls_b, qb_b);
+    while (on_a) {
+      const uint8_t *sq_c, *sq_d;
+      uint32_t ls_c, ls_d, qb_c[kQualPre], qb_d[kQualPre];
+      const bool on_c = fetch(sq_c, ls_c, qb_c), on_d = fetch(sq_d, ls_d, qb_d);
+      tally(sq_a, ls_a, qb_a);
+      if (on_b) tally(sq_b, ls_b, qb_b);
+      sq_a = sq_c; ls_a = ls_c; on_a = on_c;
+      sq_b = sq_d; ls_b = ls_d; on_b = on_d;
 #pragma unroll
-      for (uint32_t k = 0; k < kQualPre; ++k) qb[k] = qb_n[k];
+      for (uint32_t k = 0; k < kQualPre; ++k) { qb_a[k] = qb_c[k]; qb_b[k] = qb_d[k]; }
     }
     __syncwarp();
     if (++steps_since_flush == kQualFlushSteps) {
