@@ -1484,6 +1484,11 @@ int ngsq_reduce(ngsq_engine* e, int root) {
   }
   rc = ngsq_refresh_results(e);
   if (rc) return rc;
+  // the `touched` flags were summed: a contig two ranks scattered into would get a depth histogram that is the sum of two
+  // partial resolves, not the histogram of the summed depth (shards must be contig-exclusive)
+  for (uint32_t c = 0; c < e->n_ref; ++c)
+    if (e->cov_enabled[c] && e->h_res[e->cov_slot[c] + COV_TOUCHED] > 1)
+      return fail(e, NGSQ_E_ARG, "reference %u holds coverage from %llu ranks: every contig must lie in one shard", c, (unsigned long long)e->h_res[e->cov_slot[c] + COV_TOUCHED]);
   CU(cudaEventRecord(e->ev_b, s));
   CU(cudaEventSynchronize(e->ev_b));
   cudaEventElapsedTime(&e->stats.ms_reduce, e->ev_a, e->ev_b);

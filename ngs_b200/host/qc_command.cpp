@@ -166,12 +166,26 @@ void run_shard(ngsq_engine* e, const std::string& path, const MappedFile& file, 
     if (shard.empty) { check(e, ngsq_set_range(e, 0, 0)); check(e, ngsq_finish(e)); return; }
     uint64_t lo, hi;
     shard_bytes(shard, file.data(), file.size(), &lo, &hi);
-    check(e, ngsq_set_range(e, shard.first_voffset, shard.end_voffset));
-    Progress progress;
     ChunkReader reader(path, chunk_bytes, direct);
-    reader.run(e, lo, hi, log_progress ? &progress : nullptr);
-    check(e, ngsq_finish(e));
-    if (log_progress) progress.report(e);
+    for (int attempt = 0;; ++attempt) {
+      check(e, ngsq_set_range(e, shard.first_voffset, shard.end_voffset));
+      Progress progress;
+      reader.run(e, lo, hi, log_progress ? &progress : nullptr);
+      const int rc = ngsq_finish(e);
+      if (rc == NGSQ_E_QUAL_CAP && attempt == 0) {
+        // a read longer than the quality-by-position table (131072 positions by default): size the table for the
+        // longest read the scan met and stream the shard again — the engine keeps nothing of a file it has streamed
+        ngsq_stats st;
+        check(e, ngsq_get_stats(e, &st));
+        info("  [*] Reads of up to " + std::to_string(st.max_read_len) + " bases: enlarging the quality table and reading the file again.");
+        check(e, ngsq_reset(e));
+        check(e, ngsq_set_quality_positions(e, (uint32_t)st.max_read_len + 1));
+        continue;
+      }
+      check(e, rc);
+      if (log_progress) progress.report(e);
+      break;
+    }
   } catch (const std::exception& ex) {
     *err = ex.what();
   }

@@ -120,6 +120,23 @@ def test_progress_lines_and_io_modes(tmp_path):
     assert perf[0]["records"] == 2_100_000 and perf[0]["wall_ms_file_to_results"] > 0 and perf[0]["waves"] >= 1
 
 
+def test_read_longer_than_the_default_quality_table_is_retried(tmp_path):
+    """One 140 kb read: the engine reports NGSQ_E_QUAL_CAP, the driver enlarges the table and streams the file again."""
+    from bamutil import rec, write_bam
+    n = 140_000
+    r = [rec(name="short", flag=0, ref=0, pos=10, mapq=30, cigar="50M", seq="ACGTA" * 10, qual=[30] * 50),
+         rec(name="ultralong", flag=0, ref=0, pos=100, mapq=30, cigar=f"{n}M", seq="ACGT" * (n // 4), qual=[7 + (i % 40) for i in range(n)])]
+    bam, bai = write_bam([("chr1", 248956422)], r)
+    p = str(tmp_path / "u.bam")
+    open(p, "wb").write(bam)
+    open(p + ".bai", "wb").write(bai)
+    res = _run(["qc", p, "GRCh38_no_alt_AnalysisSet", "-o", str(tmp_path), "-p", "u"])
+    assert "enlarging the quality table" in res.stderr
+    want_path = str(tmp_path / "o.json")
+    oracle_ints(np.frombuffer(bam, dtype=np.uint8), np.frombuffer(bai, dtype=np.uint8), json_path=want_path)
+    assert canonical_results(str(tmp_path / "u.results.json")) == canonical_results(want_path)
+
+
 def _n_gpus():
     try:
         import torch
