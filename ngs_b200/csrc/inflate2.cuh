@@ -127,12 +127,12 @@ __device__ __forceinline__ void resolve_copy_win(uint8_t* ob, uint8_t* wptr, uin
     const uint32_t n = min(min(8u, D), mlen - done);
     const uint32_t d0 = pos + done, s0 = d0 - D;  // block-relative
     uint2 v;
-    if (s0 >= w0) v = load8_unaligned(wptr + (s0 - w0), n);
-    else if (s0 + n <= w0) v = load8_unaligned(ob + s0, n);
-    else {  // the source straddles the start of the window
+    if (s0 >= w0 && s0 + n <= w1) v = load8_unaligned(wptr + (s0 - w0), n);
+    else if (s0 + n <= w0 || s0 >= w1) v = load8_unaligned(ob + s0, n);  // before the window, or the tail of a match that ran past it
+    else {  // the source straddles an end of the window
       v = make_uint2(0, 0);
       for (uint32_t k = 0; k < n; ++k) {
-        const uint32_t byte = s0 + k >= w0 ? wptr[s0 + k - w0] : ob[s0 + k];
+        const uint32_t byte = (s0 + k >= w0 && s0 + k < w1) ? wptr[s0 + k - w0] : ob[s0 + k];
         if (k < 4) v.x |= byte << (8 * k); else v.y |= byte << (8 * (k - 4));
       }
     }
@@ -202,7 +202,7 @@ inflate_resolve_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ 
       uint8_t* const abase = gbase - mis;
       uint8_t* const win = s_win[wic];
       uint8_t* const wptr = win + mis;
-      const uint32_t n_chunks = (mis + (w1 - w0) + 15) >> 4;
+      const uint32_t n_chunks = (mis + (w1 - w0) + 2 + 15) >> 4;  // + 2: the 3-byte token of a match that starts on the window's last bytes
       for (uint32_t c = lane; c < n_chunks; c += 32) *reinterpret_cast<uint4*>(win + 16 * c) = *reinterpret_cast<const uint4*>(abase + 16 * c);
 #endif
       __syncwarp();
