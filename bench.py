@@ -174,6 +174,10 @@ def cpu_sample(args, wl):
     sample is a smaller logical BAM of the same shape, sized for the same number of BASES."""
     from ngs_b200 import ffi
     shape, total, level = wl["shape"], wl["per_gpu"], wl["level"]
+    if shape == 3:
+        # spliced reads: the reference's Coverage.process is O(span) and 60 % of these records span a ~100 kb intron
+        # (coverage.rs:165-178 walks every skipped position): 3 M records would be minutes of one core
+        args = argparse.Namespace(**{**vars(args), "cpu_sample": min(args.cpu_sample, 400_000)})
     if shape == 2:
         n = max(2000, min(total, args.cpu_sample * 300 // 56000))
         bam, bai, info = ffi.synth_bam(shape, n, level=level)
