@@ -107,6 +107,8 @@ struct ngsq_engine {
 
   // results: [fixed | per-contig coverage slots | quality table, qpos_cap rows]
   uint64_t* d_res = nullptr;
+  LongRead* d_long = nullptr;        // the wave's reads longer than the facet kernel's shared-memory quality tables
+  uint64_t long_cap = 0;
   size_t res_words = 0, res_cap_words = 0;
   uint32_t qual_off = R_FIXED_WORDS;
   uint32_t qpos_cap = 0;
@@ -478,6 +480,13 @@ int ensure_wave_buffers(ngsq_engine* e, int s, uint32_t n, uint64_t bytes) {
     if ((rc = fresh(e, e->d_rec, need_rec, "record table"))) return rc;
     e->rec_cap = need_rec;
   }
+  // a read with more than kQualSmemPositions bases takes more than 260 bytes
+  const uint64_t need_long = (e->headroom + std::max<uint64_t>(e->slot_cap[0], e->slot_cap[1])) / 260 + 2;
+  if ((e->cfg.flags & NGSQ_F_RECORD_FACETS) && need_long > e->long_cap) {
+    if ((rc = quiesce())) return rc;
+    if ((rc = fresh(e, e->d_long, need_long, "long-read list"))) return rc;
+    e->long_cap = need_long;
+  }
   if ((e->cfg.flags & NGSQ_F_COVERAGE) && e->cfg.max_records && need_rec > e->mark_cap) {
     if ((rc = quiesce())) return rc;
     if ((rc = fresh(e, e->d_mark, need_rec, "record marks"))) return rc;
@@ -595,12 +604,23 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
     P.res = e->d_res; P.qual = e->d_res + e->qual_off;
     P.qpos_smem = kQualSmemPositions;
     P.qpos_cap = e->qpos_cap;
+    P.long_list = e->d_long; P.long_cap = (uint32_t)std::min<uint64_t>(e->long_cap, 0xFFFFFFFFu);
     // persistent grid sized for the bound "a record is at least 36 bytes": the record count stays on the device
     const uint64_t want = (bytes / 36 + 2 + kFacetThreads - 1) / kFacetThreads;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)e->n_sm * e->facet_occ);
     facets_kernel<<<grid, kFacetThreads, e->facet_smem, st>>>(P);
     CU(cudaGetLastError());
     e->other_launches++;
+    if (e->cfg.flags & NGSQ_F_RECORD_FACETS) {
+      // quality positions beyond the shared-memory tables; both kernels return at once on a wave without such reads
+      QualTileParams T{};
+      T.d = slot; T.list = e->d_long; T.long_cap = P.long_cap; T.st = e->d_state; T.qual = P.qual; T.res = e->d_res;
+      T.qpos_smem = kQualSmemPositions; T.qpos_cap = e->qpos_cap;
+      qual_tiles_kernel<<<e->n_sm * 2, kTileThreads, kTileSmem, st>>>(T);
+      qual_verdict_kernel<<<e->n_sm, 256, 0, st>>>(T);
+      CU(cudaGetLastError());
+      e->other_launches += 2;
+    }
   }
   if (cov_n) {
     CovNParams C{};
@@ -748,6 +768,7 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   CUC(cudaFuncSetAttribute(inflate_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem));
   e->facet_smem = (size_t)qual_table_bytes(kQualSmemPositions) * (kFacetThreads / 32) + (size_t)(kTlenPad + kGcPad + kCigWords) * 4;
   CUC(cudaFuncSetAttribute(facets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->facet_smem));
+  CUC(cudaFuncSetAttribute(qual_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
   CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->facet_occ, facets_kernel, kFacetThreads, e->facet_smem));
   if (e->facet_occ < 1) e->facet_occ = 1;
   {
@@ -776,7 +797,7 @@ void ngsq_destroy(ngsq_engine* e) {
   for (auto& c : e->chunks) cudaEventDestroy(c.copied);
   for (auto& p : e->waves) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.resolved, p.scan_end, p.facets_end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
   for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_d, e->ev_e, e->ev_f, e->ev_g}) if (ev) cudaEventDestroy(ev);
-  void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_tile_off, e->d_tile_sum, e->d_res, e->d_slot[0], e->d_slot[1],
+  void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_tile_off, e->d_tile_sum, e->d_res, e->d_long, e->d_slot[0], e->d_slot[1],
                   e->d_blocks_all, e->d_crc_all, e->d_wstatus, e->d_first, e->d_landed, e->d_count, e->d_base,
                   e->d_bitmap, e->d_rec, e->d_mark, e->d_queue, e->d_state, e->d_crc_tables};
   for (void* p : ptrs) if (p) cudaFree(p);

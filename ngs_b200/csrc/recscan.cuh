@@ -67,7 +67,8 @@ struct RunState {
   // ---- current wave ----
   uint64_t carry_voff;      // virtual offset of the record carried INTO this wave
   uint32_t carry_len, pad4; // its bytes in front of the wave's first block
-  uint32_t wave_chain, wave_bad, wave_trunc, redo, wave_end_reached, pad0;
+  uint32_t wave_chain, wave_bad, wave_trunc, redo, wave_end_reached;
+  uint32_t wave_long;       // reads longer than the facet kernel's shared-memory quality tables (facets.cuh: LongRead list)
   uint64_t next_carry;      // slot offset where the walk that reached the end of the wave stopped
   uint64_t next_carry_voff;
   // ---- pass-2 `-n` (cov_n.cuh): query-yielded records so far, reference id + 1 of the last one ----
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(1024) wave_begin_kernel(RunState* st, uint8_t*
     if (st->end_pending) st->end_reached = 1;
     st->rec_base += st->wave_rec;
     st->wave_rec = 0;
-    st->wave_chain = st->wave_bad = st->wave_trunc = st->redo = st->wave_end_reached = 0;
+    st->wave_chain = st->wave_bad = st->wave_trunc = st->redo = st->wave_end_reached = st->wave_long = 0;
     st->next_carry = kNoCarry;
     st->waves++;
   }

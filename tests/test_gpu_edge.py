@@ -192,3 +192,63 @@ def test_truncated_input():
     bam, bai = write_bam(REFS, _records(seed=10), block_payload=5000, with_eof=False)
     e = _engine_error(bam[:-100])
     assert e.code == -3
+
+
+def _mixed_length_records(seed, n=260):
+    """Reads on both sides of the facet kernel's shared-memory quality tables (152 positions) and of the tile width of
+    the pass that tallies the rest (256): some without qualities, some whose only real bytes sit in the tail."""
+    rng = np.random.default_rng(seed)
+    out, pos = [], 0
+    lengths = [100, 151, 152, 153, 200, 250, 407, 408, 409, 663, 664, 665, 1000, 3000, 7001]
+    for i in range(n):
+        L = lengths[i % len(lengths)] if i % 4 else int(rng.integers(1, 2500))
+        pos += int(rng.integers(0, 300))
+        seq = "".join(rng.choice(list("ACGT"), size=L))
+        kind = i % 11
+        if kind == 3:
+            qual = None                                   # absent: every byte 0xFF
+        elif kind == 7:
+            qual = rng.integers(0, 3, size=L).tolist()    # piles on few counters
+        else:
+            qual = rng.integers(0, 94, size=L).tolist()
+        out.append(rec(name=f"m{i}", flag=int(rng.choice([0x0, 0x10, 0x63, 0x93])), ref=0, pos=pos, mapq=60, cigar=f"{L}M",
+                       next_ref=0, next_pos=pos + 50, tlen=300, seq=seq, qual=qual))
+    return out
+
+
+@pytest.mark.parametrize("payload,launch_blocks", [(0xFF00, 0), (20000, 3)])
+def test_quality_positions_beyond_the_shared_memory_tables(payload, launch_blocks):
+    refs = [("chr1", 2_000_000)]
+    bam, bai = write_bam(refs, _mixed_length_records(21), block_payload=payload)
+    b, i = as_u8(bam), as_u8(bai)
+    want = oracle_ints(b, i, gc_seed=3)
+    got = engine_ints(b, gc_seed=3, launch_blocks=launch_blocks)
+    assert want["quality"].shape[0] == 7001
+    assert_same_ints(got, want)
+
+
+@pytest.mark.parametrize("where", [10, 151, 152, 300, 407, 408, 2999])
+def test_quality_above_93_anywhere_in_a_long_read_fails_the_run(where):
+    q = [30] * 3000
+    q[where] = 94
+    r = [rec(name="ok", flag=0, ref=0, pos=1, cigar="200M", seq="A" * 200, qual=[20] * 200),
+         rec(name="bad", flag=0, ref=0, pos=5, cigar="3000M", seq="C" * 3000, qual=q)]
+    bam, bai = write_bam(REFS, r)
+    assert _engine_error(bam).code == -7
+
+
+@pytest.mark.parametrize("where", [0, 151, 152, 2999])
+def test_a_single_real_byte_makes_a_long_quality_string_present_and_its_0xff_bytes_invalid(where):
+    """quality_scores.rs:37-49 with noodles' presence rule: all-0xFF means absent; one real byte makes the
+    string present, and then every 0xFF in it is a score of 255 > 93."""
+    q = [0xFF] * 3000
+    q[where] = 40
+    r = [rec(name="odd", flag=0, ref=0, pos=5, cigar="3000M", seq="C" * 3000, qual=q)]
+    bam, bai = write_bam(REFS, r)
+    assert _engine_error(bam).code == -7
+    # ... while the all-0xFF string is simply absent: the table stays empty beyond the other read
+    r = [rec(name="short", flag=0, ref=0, pos=1, cigar="100M", seq="A" * 100, qual=[20] * 100),
+         rec(name="absent", flag=0, ref=0, pos=5, cigar="3000M", seq="C" * 3000, qual=None)]
+    bam, bai = write_bam(REFS, r)
+    got = _check(bam, bai)
+    assert got["quality"].shape[0] == 100

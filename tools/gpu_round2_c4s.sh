@@ -2,7 +2,7 @@
 # GPU call: long-read paths after a kernel change — the long-read tests, then configs[3]'s shape at a quarter of its size.
 set -u
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_gpu_stream.py tests/test_gpu_host_driver.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -5)
+(timeout 600 python -m pytest tests/test_gpu_edge.py tests/test_gpu_stream.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -15)
 (timeout 600 python bench.py --shape c4 --records 500000 --steps 2 --warmup 3 --cpu-sample 20000) > gpurun_out/r2_bench_c4s.json 2> gpurun_out/r2_bench_c4s.err; echo "rc=$?"
 grep -E "generated|warm-up|resident steps|e2e steps|Error|error" gpurun_out/r2_bench_c4s.err | tail -8
 python - <<'PY'
