@@ -423,8 +423,8 @@ int launch_inflate(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_t*
   CU(cudaMemsetAsync(bitmap, 0, (size_t)n * kBitmapWords * 4, s));
   CU(cudaMemsetAsync(status, 0, (size_t)n * 4, s));
   CU(cudaMemsetAsync(queue, 0, 4, s));
-  const uint32_t per_cta = kDecThreads;
-  uint32_t grid = std::min<uint32_t>((n + per_cta - 1) / per_cta, (uint32_t)e->n_sm);
+  // one CTA per SM as soon as there is a batch of 32 blocks for each (the kernel interleaves batches over the CTAs)
+  uint32_t grid = std::min<uint32_t>((n + 31) / 32, (uint32_t)e->n_sm);
   if (ev_decode_from) CU(cudaEventRecord(ev_decode_from, s));
   inflate_decode_kernel<<<grid, kDecThreads, kDecSmem, s>>>(out, blocks, n, queue, status, bitmap);
   CU(cudaGetLastError());

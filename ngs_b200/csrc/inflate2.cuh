@@ -43,10 +43,21 @@ inflate_decode_kernel(uint8_t* __restrict__ out, const BlockDesc* __restrict__ b
   __syncthreads();
   L.lut = s_base_lut;
 #endif
+  // First batch of every warp: static and interleaved over the CTAs (warp w of CTA c takes batch w * grid + c), so that a
+  // partial wave — the tail of a run — spreads over all SMs with few warps each instead of filling a few SMs with 18: a
+  // lane decodes its block serially, and a warp that shares its scheduler with four others runs at a fraction of the
+  // speed of one that does not.  Later batches (launches larger than the grid) come from the queue.
+  const uint32_t static_blocks = gridDim.x * (uint32_t)kDecWarps * 32u;
+  bool first = true;
   for (;;) {
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(queue, 32u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (first) {
+      base = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u;
+      first = false;
+    } else {
+      if (lane == 0) base = static_blocks + atomicAdd(queue, 32u);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    }
     if (base >= n_blocks) break;
     const uint32_t b = base + lane;
     if (b < n_blocks) L.begin_block(blocks[b], out, bitmap + (size_t)b * kBitmapWords);
