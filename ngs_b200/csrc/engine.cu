@@ -5,10 +5,12 @@
 //   compressed staging ring | 2 x [headroom | one wave of inflated bytes] | match bitmap of a wave | per-wave block
 //   tables | record offset table of a wave (8 B/record) | per-contig int32 difference arrays | packed u64 result
 //   buffer (the NCCL payload) | RunState (everything that links two waves, recscan.cuh).
-// Streams: H2D copies on s_copy, kernels on s_comp, the per-block CRC32 check on s_aux (it depends only on the inflated
-// bytes, so it runs beside the record scan and the facet kernels).  A wave is enqueued without any host round trip:
-// the submitting thread never waits for the GPU, the PCIe copy of chunk k+1 overlaps the kernels of wave k, and after
-// the last chunk has arrived only the last (small) wave, the coverage resolve and the result read-back remain.
+// Streams: H2D copies on s_copy; inflate (decode + resolve) on s_comp; record scan + facet kernels on s_scan, beside the
+// inflate of the NEXT wave (the decoder owns the SMs' shared memory but leaves room for the scan kernels; the facet kernels
+// share the SMs with the resolve kernel); the per-block CRC32 check on s_aux, enqueued behind the start of the next
+// wave's decode.  A wave is enqueued without any host round trip: the submitting thread never waits for the GPU, the PCIe
+// copy of chunk k+1 overlaps the kernels of wave k, and after the last chunk has arrived only the last (small) wave,
+// the coverage resolve and the result read-back remain.
 #include <dlfcn.h>
 #include <time.h>
 
@@ -78,7 +80,7 @@ struct ngsq_engine {
   int n_sm = 0;
   ngsq_config cfg{};
   std::string err;
-  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_scan = nullptr, s_aux = nullptr;
   cudaEvent_t ev_start = nullptr, ev_a = nullptr, ev_b = nullptr, ev_d = nullptr, ev_e = nullptr, ev_f = nullptr, ev_g = nullptr;
   bool run_started = false, finished = false;
 
@@ -131,7 +133,7 @@ struct ngsq_engine {
   size_t comp_total = 0;
 
   // waves
-  struct Wave { cudaEvent_t begin, decoded_from, decoded, resolved, scan_end, facets_end, crc_begin, crc_end; uint32_t b1; bool scanned; };
+  struct Wave { cudaEvent_t begin, decoded_from, decoded, resolved, scan_begin, begun, scan_end, facets_end, crc_begin, crc_end; uint32_t b0, b1; bool scanned, crc_launched; const uint8_t* out; };
   std::vector<Wave> waves;
   uint32_t headroom = 0;
   uint8_t* d_slot[2] = {nullptr, nullptr};
@@ -143,7 +145,7 @@ struct ngsq_engine {
   uint32_t blocks_all_cap = 0;
   struct PinSlab { uint8_t* p; size_t cap, used; };
   std::vector<PinSlab> pin_slabs;    // pinned staging of those uploads (lives until ngsq_reset)
-  uint32_t *d_wstatus = nullptr, *d_first = nullptr, *d_landed = nullptr, *d_count = nullptr;
+  uint32_t *d_wstatus[2] = {nullptr, nullptr}, *d_first = nullptr, *d_landed = nullptr, *d_count = nullptr;
   uint64_t* d_base = nullptr;
   uint32_t scan_cap = 0;
   uint32_t* d_bitmap = nullptr;
@@ -353,6 +355,7 @@ int upload_descriptors(ngsq_engine* e, uint32_t first, uint32_t end) {
     // the table is sized by reserve_blocks; without it, it doubles (rare: everything in flight is awaited first)
     CU(cudaStreamSynchronize(e->s_copy));
     CU(cudaStreamSynchronize(e->s_comp));
+    CU(cudaStreamSynchronize(e->s_scan));
     CU(cudaStreamSynchronize(e->s_aux));
     const uint32_t cap = std::max<uint32_t>(end + end / 2, std::max<uint32_t>(e->cfg.reserve_blocks, 1u << 18));
     BlockDesc* nb = nullptr;
@@ -430,8 +433,10 @@ int launch_inflate(ngsq_engine* e, const BlockDesc* blocks, uint32_t n, uint8_t*
   CU(cudaGetLastError());
   if (ev_decoded) CU(cudaEventRecord(ev_decoded, s));
   // full occupancy (8 CTAs x 8 warps per SM): measured 39 ms / 40 M records vs 47 / 56 / 79 ms with 4 / 3 / 2 CTAs per SM —
-  // latency hiding beats keeping the blocks in flight L2-resident
-  uint32_t rgrid = std::min<uint32_t>((n + kResWarps - 1) / kResWarps, (uint32_t)e->n_sm * 8);
+  // latency hiding beats keeping the blocks in flight L2-resident.  One block per warp, no grid-stride loop: the facet
+  // kernels of the previous wave share the SMs with this kernel (scan stream), and CTAs that start late must not carry
+  // a fixed share of the blocks.
+  uint32_t rgrid = (n + kResWarps - 1) / kResWarps;
   inflate_resolve_kernel<<<rgrid, kResThreads, 0, s>>>(out, blocks, n, bitmap, status);
   CU(cudaGetLastError());
   return NGSQ_OK;
@@ -444,6 +449,7 @@ int ensure_wave_buffers(ngsq_engine* e, int s, uint32_t n, uint64_t bytes) {
   auto quiesce = [&]() -> int {
     if (synced) return NGSQ_OK;
     CU(cudaStreamSynchronize(e->s_comp));
+    CU(cudaStreamSynchronize(e->s_scan));
     CU(cudaStreamSynchronize(e->s_aux));
     synced = true;
     return NGSQ_OK;
@@ -461,7 +467,8 @@ int ensure_wave_buffers(ngsq_engine* e, int s, uint32_t n, uint64_t bytes) {
   if (n > e->scan_cap) {
     if ((rc = quiesce())) return rc;
     const uint32_t cap = std::max<uint32_t>(n + n / 8, std::min<uint32_t>(launch_quantum(e), std::max<uint32_t>(e->cfg.reserve_blocks, 64u)));
-    if ((rc = fresh(e, e->d_wstatus, cap, "status"))) return rc;
+    if ((rc = fresh(e, e->d_wstatus[0], cap, "status"))) return rc;
+    if ((rc = fresh(e, e->d_wstatus[1], cap, "status"))) return rc;
     if ((rc = fresh(e, e->d_first, cap, "scan tables"))) return rc;
     if ((rc = fresh(e, e->d_landed, cap, "scan tables"))) return rc;
     if ((rc = fresh(e, e->d_count, (size_t)cap + 1, "scan tables"))) return rc;
@@ -496,7 +503,28 @@ int ensure_wave_buffers(ngsq_engine* e, int s, uint32_t n, uint64_t bytes) {
 }
 
 int new_wave_events(ngsq_engine* e, ngsq_engine::Wave& w) {
-  for (cudaEvent_t* x : {&w.begin, &w.decoded_from, &w.decoded, &w.resolved, &w.scan_end, &w.facets_end, &w.crc_begin, &w.crc_end}) CU(cudaEventCreate(x));
+  for (cudaEvent_t* x : {&w.begin, &w.decoded_from, &w.decoded, &w.resolved, &w.scan_begin, &w.begun, &w.scan_end, &w.facets_end, &w.crc_begin, &w.crc_end}) CU(cudaEventCreate(x));
+  return NGSQ_OK;
+}
+
+// CRC32 of a wave's blocks against their trailers (what noodles-bgzf checks per block), on its own stream.  The kernel's
+// shared-memory tables cannot share an SM with the decoder, and a CRC kernel that reached the SMs first would hold the
+// next wave's decode back; so it is enqueued behind the START of the next wave's decode (`after`; lowest stream
+// priority) and fills the SMs as the decoder leaves them, beside that wave's resolve.  The last wave's follows it at once.
+int launch_crc(ngsq_engine* e, ngsq_engine::Wave& w, cudaEvent_t after) {
+  if (w.crc_launched) return NGSQ_OK;
+  w.crc_launched = true;
+  CU(cudaStreamWaitEvent(e->s_aux, w.resolved, 0));
+  if (after) CU(cudaStreamWaitEvent(e->s_aux, after, 0));
+  CU(cudaEventRecord(w.crc_begin, e->s_aux));
+  if (e->cfg.flags & NGSQ_F_VERIFY_CRC) {
+    const uint32_t n = w.b1 - w.b0;
+    const uint32_t grid = (n + kCrcThreads / 32 - 1) / (kCrcThreads / 32);  // one block per warp: late CTAs carry no fixed share
+    crc32_kernel<<<grid, kCrcThreads, kCrcSmem, e->s_aux>>>(w.out, e->d_blocks_all + w.b0, e->d_crc_all + w.b0, n, e->d_crc_tables, &e->d_state->crc_bad);
+    CU(cudaGetLastError());
+    e->other_launches++;
+  }
+  CU(cudaEventRecord(w.crc_end, e->s_aux));
   return NGSQ_OK;
 }
 
@@ -516,11 +544,17 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
     if (!wi) e->host_t0 = now;
     e->host_ms.push_back(now - e->host_t0);
   }
+  // Two kernel streams: inflate (decode + resolve) on s_comp, record scan + facet kernels on s_scan, so that the scan of
+  // wave k runs beside the decode of wave k + 1 (the decoder owns the SMs' shared memory but leaves thread and register
+  // room) and its facet kernels beside the resolve of wave k + 1.
   cudaStream_t st = e->s_comp;
   const uint64_t out0 = e->h_blocks[b0].out_off;
   const uint64_t bytes = e->h_blocks[b1 - 1].out_off + e->h_blocks[b1 - 1].isize - out0;
-  // slot s and its tables were last used by wave wi - 2: its CRC kernel (own stream) must be done with them
+  // slot s and the status table of this parity were last used by wave wi - 2: its CRC kernel (own stream), its scan and
+  // facet kernels, and the copy of its open record into wave wi - 1's headroom (`begun` of wave wi - 1 is recorded
+  // behind all of these on the in-order scan stream) must be done with them
   if (wi >= 2) CU(cudaStreamWaitEvent(st, e->waves[wi - 2].crc_end, 0));
+  if (wi >= 1) CU(cudaStreamWaitEvent(st, e->waves[wi - 1].begun, 0));
   if ((rc = ensure_wave_buffers(e, s, n, bytes))) return rc;
   // the compressed bytes of the wave: wait for the copy of the last chunk it reads
   for (const auto& c : e->chunks)
@@ -533,30 +567,27 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
   uint8_t* out = slot + e->headroom - out0;
   const BlockDesc* wblocks = e->d_blocks_all + b0;
   CU(cudaEventRecord(w.begin, st));
-  rc = launch_inflate(e, wblocks, n, out, e->d_queue, e->d_wstatus, e->d_bitmap, st, w.decoded_from, w.decoded);
+  uint32_t* wstatus = e->d_wstatus[s];
+  rc = launch_inflate(e, wblocks, n, out, e->d_queue, wstatus, e->d_bitmap, st, w.decoded_from, w.decoded);
   if (rc) return rc;
   e->other_launches += 1;  // resolve kernel (the decode kernel is counted as the inflate launch)
   CU(cudaEventRecord(w.resolved, st));
-  // CRC32 of the wave's blocks against their trailers (what noodles-bgzf checks per block), on its own stream: it
-  // overlaps the record scan and the facet kernels of this wave and the decode of the next one
-  CU(cudaStreamWaitEvent(e->s_aux, w.resolved, 0));
-  CU(cudaEventRecord(w.crc_begin, e->s_aux));
-  if (e->cfg.flags & NGSQ_F_VERIFY_CRC) {
-    const uint32_t grid = std::min<uint32_t>((n + kCrcThreads / 32 - 1) / (kCrcThreads / 32), (uint32_t)e->n_sm * 6);
-    crc32_kernel<<<grid, kCrcThreads, kCrcSmem, e->s_aux>>>(out, wblocks, e->d_crc_all + b0, n, e->d_crc_tables, &e->d_state->crc_bad);
-    CU(cudaGetLastError());
-    e->other_launches++;
-  }
-  CU(cudaEventRecord(w.crc_end, e->s_aux));
+  // the previous wave's CRC kernel becomes eligible when this wave's decode starts (see launch_crc)
+  w.b0 = b0; w.out = out; w.crc_launched = false;
+  if (wi >= 1 && (rc = launch_crc(e, e->waves[wi - 1], w.decoded_from))) return rc;
 
   // ---- K3: which part of the wave does the shard own?
   const bool before_start = !e->start_resolved || e->start_block >= b1;
   const bool after_end = e->end_resolved && e->end_block < b0;
   w.scanned = !before_start && !after_end;
+  st = e->s_scan;
+  CU(cudaStreamWaitEvent(st, w.resolved, 0));
+  CU(cudaEventRecord(w.scan_begin, st));
   if (!w.scanned) {
-    status_fold_kernel<<<(n + 255) / 256, 256, 0, st>>>(e->d_wstatus, n, b0, e->d_state);
+    status_fold_kernel<<<(n + 255) / 256, 256, 0, st>>>(wstatus, n, b0, e->d_state);
     CU(cudaGetLastError());
     e->other_launches++;
+    CU(cudaEventRecord(w.begun, st));
     CU(cudaEventRecord(w.scan_end, st));
     CU(cudaEventRecord(w.facets_end, st));
     e->waves.push_back(w);
@@ -564,7 +595,7 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
     return NGSQ_OK;
   }
   WaveParams W{};
-  W.d = slot; W.out0 = out0; W.blocks = wblocks; W.status = e->d_wstatus; W.n_blocks = n; W.first_global = b0; W.headroom = e->headroom;
+  W.d = slot; W.out0 = out0; W.blocks = wblocks; W.status = wstatus; W.n_blocks = n; W.first_global = b0; W.headroom = e->headroom;
   W.first_wave = e->start_block >= b0 ? 1u : 0u;
   W.final_wave = final_wave ? 1u : 0u;
   W.n_ref = (int32_t)e->n_ref;
@@ -577,15 +608,18 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
   // the previous scanned wave sits in the other slot (waves outside the range carry nothing)
   const uint8_t* prev = (wi && e->waves[wi - 1].scanned) ? e->d_slot[s ^ 1] : nullptr;
   CU(cudaMemsetAsync(e->d_landed, 0, (size_t)n * 4, st));
-  wave_begin_kernel<<<1, 1024, 0, st>>>(e->d_state, slot, prev, e->headroom, W.first_wave);
+  // single-CTA kernels of the scan chain use 256 threads: beside a resident decoder CTA (576 threads x 96 registers, all
+  // but 4 KB of the shared memory) an SM has room for about 10 K registers
+  wave_begin_kernel<<<1, 256, 0, st>>>(e->d_state, slot, prev, e->headroom, W.first_wave);
+  CU(cudaEventRecord(w.begun, st));  // the other slot is free for the next wave's inflate
   find_first_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(W);
   const uint32_t wg = (n + 1 + 127) / 128;
   walk_kernel<false, false><<<wg, 128, 0, st>>>(W);
   check_landed_kernel<false><<<(n + 255) / 256, 256, 0, st>>>(W);
-  chain_fix_kernel<<<1, 1024, 0, st>>>(W);
+  chain_fix_kernel<<<1, 256, 0, st>>>(W);
   walk_kernel<false, true><<<wg, 128, 0, st>>>(W);
   check_landed_kernel<true><<<(n + 255) / 256, 256, 0, st>>>(W);
-  scan_counts_kernel<<<1, 1024, 0, st>>>(W);
+  scan_counts_kernel<<<1, 256, 0, st>>>(W);
   walk_kernel<true, false><<<wg, 128, 0, st>>>(W);
   CU(cudaGetLastError());
   e->other_launches += 9;
@@ -754,8 +788,16 @@ int ngsq_create(int device, const ngsq_config* cfg, ngsq_engine** out) {
   CUC(cudaGetDeviceProperties(&prop, device));
   e->n_sm = prop.multiProcessorCount;
   CUC(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
-  CUC(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
-  CUC(cudaStreamCreateWithFlags(&e->s_aux, cudaStreamNonBlocking));
+  {
+    // Which kernel gets an SM when several wait for one: the scan stream's first (short kernels that gate the reuse of a
+    // slot), inflate next, the CRC check last (numerically lower = higher priority)
+    int prio_low = 0, prio_high = 0;
+    CUC(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+    const int prio_mid = prio_high < prio_low - 1 ? prio_low - 1 : prio_high;
+    CUC(cudaStreamCreateWithPriority(&e->s_scan, cudaStreamNonBlocking, prio_high));
+    CUC(cudaStreamCreateWithPriority(&e->s_comp, cudaStreamNonBlocking, prio_mid));
+    CUC(cudaStreamCreateWithPriority(&e->s_aux, cudaStreamNonBlocking, prio_low));
+  }
   for (cudaEvent_t* ev : {&e->ev_start, &e->ev_a, &e->ev_b, &e->ev_d, &e->ev_e, &e->ev_f, &e->ev_g}) CUC(cudaEventCreate(ev));
   CUC(cudaMalloc(&e->d_queue, 64));
   CUC(cudaMalloc(&e->d_state, sizeof(RunState)));
@@ -795,10 +837,10 @@ void ngsq_destroy(ngsq_engine* e) {
   cudaDeviceSynchronize();
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto& c : e->chunks) cudaEventDestroy(c.copied);
-  for (auto& p : e->waves) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.resolved, p.scan_end, p.facets_end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
+  for (auto& p : e->waves) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.resolved, p.scan_begin, p.begun, p.scan_end, p.facets_end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
   for (cudaEvent_t ev : {e->ev_start, e->ev_a, e->ev_b, e->ev_d, e->ev_e, e->ev_f, e->ev_g}) if (ev) cudaEventDestroy(ev);
   void* ptrs[] = {e->d_ref_len, e->d_cov_enabled, e->d_diff_base, e->d_cov_slot, e->d_diff, e->d_tile, e->d_tile_off, e->d_tile_sum, e->d_res, e->d_long, e->d_slot[0], e->d_slot[1],
-                  e->d_blocks_all, e->d_crc_all, e->d_wstatus, e->d_first, e->d_landed, e->d_count, e->d_base,
+                  e->d_blocks_all, e->d_crc_all, e->d_wstatus[0], e->d_wstatus[1], e->d_first, e->d_landed, e->d_count, e->d_base,
                   e->d_bitmap, e->d_rec, e->d_mark, e->d_queue, e->d_state, e->d_crc_tables};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (e->h_state) cudaFreeHost(e->h_state);
@@ -812,6 +854,7 @@ void ngsq_destroy(ngsq_engine* e) {
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
   if (e->s_comp) cudaStreamDestroy(e->s_comp);
   if (e->s_aux) cudaStreamDestroy(e->s_aux);
+  if (e->s_scan) cudaStreamDestroy(e->s_scan);
   delete e;
 }
 
@@ -820,11 +863,12 @@ int ngsq_reset(ngsq_engine* e) {
   CU(cudaSetDevice(e->device));
   CU(cudaStreamSynchronize(e->s_copy));
   CU(cudaStreamSynchronize(e->s_comp));
+  CU(cudaStreamSynchronize(e->s_scan));
   CU(cudaStreamSynchronize(e->s_aux));
   for (auto& c : e->chunks) cudaEventDestroy(c.copied);
   e->chunks.clear();
   e->launched = 0;
-  for (auto& p : e->waves) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.resolved, p.scan_end, p.facets_end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
+  for (auto& p : e->waves) for (cudaEvent_t x : {p.begin, p.decoded_from, p.decoded, p.resolved, p.scan_begin, p.begun, p.scan_end, p.facets_end, p.crc_begin, p.crc_end}) cudaEventDestroy(x);
   e->waves.clear();
   e->h_blocks.clear(); e->h_crc.clear();
   for (auto& sg : e->comp_segs) { sg.used = 0; sg.blocks_end = 0; }
@@ -1168,6 +1212,11 @@ int ngsq_finish(ngsq_engine* e) {
     if (e->end_voff && !e->end_resolved && (e->end_voff & 0xFFFF)) return fail(e, NGSQ_E_ARG, "virtual offset %llu is beyond the submitted data", (unsigned long long)e->end_voff);
   }
   cudaStream_t s = e->s_comp;
+  if (!e->waves.empty()) {
+    int crc_rc = launch_crc(e, e->waves.back(), nullptr);
+    if (crc_rc) return crc_rc;
+    CU(cudaStreamWaitEvent(s, e->waves.back().facets_end, 0));  // the scan stream's last kernel
+  }
   CU(cudaEventRecord(e->ev_d, s));
   // K9
   if (e->cfg.flags & NGSQ_F_COVERAGE) {
@@ -1231,7 +1280,7 @@ int ngsq_finish(ngsq_engine* e) {
     cudaEventElapsedTime(&ms, p.decoded_from, p.decoded); st.ms_inflate_decode += ms;
     cudaEventElapsedTime(&ms, p.decoded, p.resolved); st.ms_inflate_resolve += ms;
     cudaEventElapsedTime(&ms, p.crc_begin, p.crc_end); st.ms_crc += ms;
-    cudaEventElapsedTime(&ms, p.resolved, p.scan_end); st.ms_scan += ms;
+    cudaEventElapsedTime(&ms, p.scan_begin, p.scan_end); st.ms_scan += ms;
     cudaEventElapsedTime(&ms, p.scan_end, p.facets_end); st.ms_facets += ms;
   }
   cudaEventElapsedTime(&st.ms_coverage, e->ev_d, e->ev_e);
@@ -1247,8 +1296,8 @@ int ngsq_finish(ngsq_engine* e) {
       if (i % 8 == 7 || i + 1 == e->chunks.size()) fprintf(stderr, "[ngsq trace] chunk %3zu copied at %8.1f (blocks < %u)\n", i, at(e->chunks[i].copied), e->chunks[i].blocks_end);
     for (size_t i = 0; i < e->waves.size(); ++i) {
       const auto& w = e->waves[i];
-      fprintf(stderr, "[ngsq trace] wave %2zu blocks<%7u host %7.1f | begin %7.1f decode %7.1f..%7.1f resolved %7.1f scan %7.1f facets %7.1f | crc %7.1f..%7.1f\n", i, w.b1,
-              i < e->host_ms.size() ? e->host_ms[i] : -1.0, at(w.begin), at(w.decoded_from), at(w.decoded), at(w.resolved), at(w.scan_end), at(w.facets_end), at(w.crc_begin), at(w.crc_end));
+      fprintf(stderr, "[ngsq trace] wave %2zu blocks<%7u host %7.1f | begin %7.1f decode %7.1f..%7.1f resolved %7.1f | scan %7.1f..%7.1f facets %7.1f | crc %7.1f..%7.1f\n", i, w.b1,
+              i < e->host_ms.size() ? e->host_ms[i] : -1.0, at(w.begin), at(w.decoded_from), at(w.decoded), at(w.resolved), at(w.scan_begin), at(w.scan_end), at(w.facets_end), at(w.crc_begin), at(w.crc_end));
     }
     fprintf(stderr, "[ngsq trace] coverage %.1f..%.1f end %.1f\n", at(e->ev_d), at(e->ev_e), at(e->ev_f));
   }

@@ -47,6 +47,9 @@ def main():
     ap.add_argument("workloads", nargs="+", help="<shape name>:<n ranks>[:<records per gpu>]")
     ap.add_argument("--workers", type=int, default=3)
     ap.add_argument("--threads", type=int, default=0, help="generator threads per worker (0 = all cores)")
+    ap.add_argument("--split", type=int, default=0,
+                    help="compute every shard in this many contig-exclusive pieces (facets are additive over them): for workloads "
+                         "whose shard file does not fit this machine's memory (configs[3]: 50 GB compressed)")
     args = ap.parse_args()
     t0 = time.perf_counter()
     for w in args.workloads:  # one workload at a time: a finished golden is on disk before the next one starts
@@ -56,7 +59,13 @@ def main():
         jobs = []
         for rank in range(n):
             mask, with_tail = bench.workload_shard(wl, rank)
-            jobs.append((wl["shape"], wl["total_records"], wl["level"], mask, with_tail, bench.GC_SEED, wl["records"], wl["coverage"], args.threads))
+            pieces = [(mask, with_tail)]
+            if args.split > 1:
+                contigs = [c for c in range(mask.bit_length()) if mask >> c & 1]
+                pieces = [(sum(1 << c for c in contigs[k::args.split]), with_tail and k == 0) for k in range(args.split)]
+                pieces = [p for p in pieces if p[0] or p[1]]
+            for m, t in pieces:
+                jobs.append((wl["shape"], wl["total_records"], wl["level"], m, t, bench.GC_SEED, wl["records"], wl["coverage"], args.threads))
         with ProcessPoolExecutor(max_workers=min(args.workers, len(jobs))) as ex:
             parts = list(ex.map(shard_ints, jobs))
         merged = merge_ints(parts, records=wl["records"], coverage=wl["coverage"])
@@ -64,7 +73,8 @@ def main():
                 "gc_seed": bench.GC_SEED, "records": sum(p["_info"]["n_records"] for p in parts),
                 "inflated_bytes": sum(p["_info"]["inflated_bytes"] for p in parts),
                 "compressed_bytes": sum(p["_info"]["compressed_bytes"] for p in parts),
-                "shard_records": [int(p["_info"]["n_records"]) for p in parts],
+                "shard_records": [int(p["_info"]["n_records"]) for p in parts] if args.split <= 1 else
+                                 [sum(int(p["_info"]["n_records"]) for p in parts)] if n == 1 else None,
                 "oracle_s": sum(p["_info"]["oracle_s"] for p in parts)}
         path = save_fullsize_golden(merged, meta)
         print(f"{w}: {meta['records']} records, oracle {meta['oracle_s']:.0f} core-seconds -> {path} ({os.path.getsize(path)} bytes)", flush=True)
