@@ -1,7 +1,9 @@
 #!/bin/bash
-# GPU call: configs[3] (long reads, 2 M records of 10-50 kb) at its named size on one GPU.
+# GPU call: configs[3] (long reads, 2 M records of 10-50 kb) at its named size on one GPU; the long-read tests first.
 set -u
 mkdir -p gpurun_out
+(timeout 600 python -m pytest tests/test_gpu_edge.py tests/test_gpu_stream.py -m gpu -x -q 2>&1 | tail -4) | tee gpurun_out/r2_c4_tests.log
+grep -q "passed" gpurun_out/r2_c4_tests.log && ! grep -q "failed" gpurun_out/r2_c4_tests.log || { echo "tests failed: no bench"; exit 1; }
 free -g | head -2 | tail -1
 (timeout 1300 python bench.py --shape c4 --steps 2 --warmup 3) > gpurun_out/r2_bench_c4.json 2> gpurun_out/r2_bench_c4.err; echo "rc=$?"
 grep -E "generated|warm-up|resident steps|e2e steps|Error|error" gpurun_out/r2_bench_c4.err | tail -8
