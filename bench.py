@@ -434,6 +434,30 @@ def main():
         del scratch
 
     log("e2e steps done")
+    # ---- the kernels' own times: one more resident pass with every kernel of a wave on ONE stream (NGSQ_F_SERIAL_STAGES).
+    # In the timed steps the scan / facet / CRC kernels of wave k share the SMs with the inflate of wave k+1, so the per-stage
+    # event times there include each other; this pass is NOT part of `value`.
+    serial = None
+    if N == 1:
+        eng_s = ffi.Engine(device=local_rank, flags=flags | ffi.NGSQ_F_SERIAL_STAGES, gc_seed=GC_SEED, reserve_inflated=D_bytes + 65536,
+                           reserve_blocks=n_blocks + 16)
+        eng_s.set_references(lens, enabled)
+        eng_s.set_range(hdr.first_voffset, 0)
+        for _ in range(2):
+            eng_s.reset()
+            eng_s.submit_device(d_comp.data_ptr(), C_bytes, blocks, n_blocks)
+            eng_s.finish()
+        ss = eng_s.stats()
+        same = "identical"
+        try:
+            assert_same_ints(collect(eng_s, lens, enabled, wl["records"], wl["coverage"]), res_resident, records=wl["records"], coverage=wl["coverage"])
+        except AssertionError as ex:
+            same = "DIFFERENT: " + " ".join(str(ex).split())[:200]
+        serial = {"ms_per_step": ss["ms_total"], "results_vs_timed_run": same,
+                  "stage_ms": {k: ss[k] for k in ["ms_inflate", "ms_inflate_decode", "ms_inflate_resolve", "ms_crc", "ms_scan", "ms_facets", "ms_coverage"]},
+                  "decode_launch_ms": ss["ms_inflate_decode"] / max(ss["inflate_launches"], 1)}
+        eng_s.close()
+        log(f"serial-stages pass: {ss['ms_total']:.1f} ms")
     # ---- max over ranks ----
     agg = torch.tensor([dev_step_ms, wall_ms, e2e_ms or 0.0, float(np.mean(infl_ms)), float(np.mean(tot_ms)), -float(np.mean(tot_ms)),
                         float(np.mean(red_ms)), -(h2d_gbs or 0.0), e2e_tail or 0.0], dtype=torch.float64, device=dev)
@@ -547,6 +571,9 @@ def main():
                        "crc_check": not args.no_crc, "waves_per_gpu": int(stats["waves"]),
                        "l2": "inputs (GBs) far exceed the 126 MB L2; no flush needed", "generation_s": gen_s,
                        "stage_ms": {k: stats[k] for k in ["ms_inflate", "ms_inflate_decode", "ms_inflate_resolve", "ms_crc", "ms_scan", "ms_facets", "ms_coverage", "ms_tail"]},
+                       "stage_ms_note": "event times inside the timed steps: the scan, facet and CRC kernels of wave k run beside the inflate of wave k+1, so the "
+                                        "stages overlap and their sum exceeds ms_per_step; `serial_stages` holds the kernels' own times (one extra pass, one stream)",
+                       "serial_stages": serial,
                        "ms_reduce": red_ms_max, "rank_ms_total": {"max": tot_ms_max, "min": -neg_tot_ms_min},
                        "stage_gbs": {"inflate (C+D)/t": (C_bytes + D_bytes) / (stats["ms_inflate"] * 1e-3) / 1e9 if stats["ms_inflate"] else None,
                                      "resolve D/t": D_bytes / (res_ms * launches * 1e-3) / 1e9 if res_ms else None,
@@ -556,6 +583,12 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "inflate_decode_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_kind": peak_kind,
                          "launch_ms": dec_ms, "launches_per_step": launches,
+                         "alone": None if not serial or not serial["decode_launch_ms"] else {
+                             "launch_ms": serial["decode_launch_ms"],
+                             "achieved": (C_bytes + D_bytes) / launches / (serial["decode_launch_ms"] * 1e-3) / 1e9,
+                             "frac": (C_bytes + D_bytes) / launches / (serial["decode_launch_ms"] * 1e-3) / 1e9 / peak,
+                             "what": "the same kernel without co-runners (serial_stages pass); `achieved` above is inside the timed steps, where the previous "
+                                     "wave's scan kernels share the SMs with it"},
                          "note": "algorithmic bytes = compressed read + inflated written per launch; Huffman decode is instruction-issue bound, not HBM-bound (DESIGN.md section 4)"},
             "cpu_baseline": cpu,
             "e2e": None if args.no_e2e else {"value": all_rec / (e2e_ms_max * 1e-3), "unit": "records/s", "h2d_bytes_per_step": int(all_C),

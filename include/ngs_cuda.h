@@ -63,6 +63,8 @@ enum {
 #define NGSQ_F_VERIFY_CRC 4u    /* verify the CRC32 of every block (reference behaviour) */
 #define NGSQ_F_EDITS 8u         /* Edits (needs ngsq_set_reference_bases for every contig that holds records) */
 #define NGSQ_F_FEATURES 16u     /* Genomic Features (needs ngsq_set_feature_model + ngsq_set_features) */
+#define NGSQ_F_SERIAL_STAGES 32u /* measurement aid: every kernel of a wave on ONE stream (no overlap with the next wave's
+                                    inflate), so that per-stage event times are the kernels' own; results are identical */
 
 typedef struct ngsq_engine ngsq_engine;
 

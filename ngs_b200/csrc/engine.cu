@@ -574,13 +574,15 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
   CU(cudaEventRecord(w.resolved, st));
   // the previous wave's CRC kernel becomes eligible when this wave's decode starts (see launch_crc)
   w.b0 = b0; w.out = out; w.crc_launched = false;
-  if (wi >= 1 && (rc = launch_crc(e, e->waves[wi - 1], w.decoded_from))) return rc;
+  const bool serial = e->cfg.flags & NGSQ_F_SERIAL_STAGES;  // measurement aid: one kernel stream, CRC beside this wave's scan
+  if (serial) { if ((rc = launch_crc(e, w, nullptr))) return rc; }
+  else if (wi >= 1 && (rc = launch_crc(e, e->waves[wi - 1], w.decoded_from))) return rc;
 
   // ---- K3: which part of the wave does the shard own?
   const bool before_start = !e->start_resolved || e->start_block >= b1;
   const bool after_end = e->end_resolved && e->end_block < b0;
   w.scanned = !before_start && !after_end;
-  st = e->s_scan;
+  st = serial ? e->s_comp : e->s_scan;
   CU(cudaStreamWaitEvent(st, w.resolved, 0));
   CU(cudaEventRecord(w.scan_begin, st));
   if (!w.scanned) {

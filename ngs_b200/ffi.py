@@ -21,6 +21,7 @@ NGSQ_F_COVERAGE = 2
 NGSQ_F_VERIFY_CRC = 4
 NGSQ_F_EDITS = 8
 NGSQ_F_FEATURES = 16
+NGSQ_F_SERIAL_STAGES = 32  # measurement aid: no overlap between the stages of consecutive waves
 
 ERROR_NAMES = {
     0: "NGSQ_OK", -1: "NGSQ_E_ARG", -2: "NGSQ_E_CUDA", -3: "NGSQ_E_TRUNCATED", -4: "NGSQ_E_BAD_BLOCK",

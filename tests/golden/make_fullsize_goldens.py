@@ -70,7 +70,7 @@ def main():
             parts = list(ex.map(shard_ints, jobs))
         merged = merge_ints(parts, records=wl["records"], coverage=wl["coverage"])
         meta = {"key": wl["key"], "shape": wl["shape"], "total_records": wl["total_records"], "level": wl["level"], "n_ranks": wl["n_ranks"],
-                "gc_seed": bench.GC_SEED, "records": sum(p["_info"]["n_records"] for p in parts),
+                "gc_seed": bench.GC_SEED, "gc_window": args.split <= 1, "records": sum(p["_info"]["n_records"] for p in parts),
                 "inflated_bytes": sum(p["_info"]["inflated_bytes"] for p in parts),
                 "compressed_bytes": sum(p["_info"]["compressed_bytes"] for p in parts),
                 "shard_records": [int(p["_info"]["n_records"]) for p in parts] if args.split <= 1 else

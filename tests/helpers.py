@@ -292,6 +292,11 @@ def compare_fullsize(got, key, n_records=None):
         return None
     if n_records is not None:
         assert int(n_records) == int(meta["records"]), f"records {n_records} != golden {meta['records']}"
-    assert_same_ints(got, want, records="general" in want, coverage="coverage" in want)
+    # a golden computed over contig-exclusive PIECES of a shard file (make_fullsize_goldens.py --split: the file does not fit
+    # the build machine's memory) saw the records at other virtual offsets than the run did: its GC window histogram is not
+    # comparable (same rule as assert_same_ints(gc_window=False)); every other integer is additive over the pieces
+    gc_window = bool(meta.get("gc_window", True))
+    assert_same_ints(got, want, records="general" in want, coverage="coverage" in want, gc_window=gc_window)
     return (f"bit-exact vs the oracle's integers on the full workload ({meta['records']} records, {meta['n_ranks']} shard file(s); "
-            f"tests/golden/fullsize_{key}.npz)")
+            f"tests/golden/fullsize_{key}.npz)" + ("" if gc_window else " except the GC window histogram, whose golden was computed over "
+            "pieces of the file at other virtual offsets (GC invariants checked; the histogram itself is covered by the sample parity)"))

@@ -143,3 +143,16 @@ def test_bai_derived_shards_of_one_file_sum_to_the_whole_file(n_shards):
     assert records == 300000
     assert_same_ints(merge_ints(parts), want, gc_window=True)
     assert any(s.end_voffset & 0xFFFF for s in shards), "no cut fell inside a block: the case is not exercised"
+
+
+def test_serial_stages_flag_changes_the_schedule_not_the_results():
+    """NGSQ_F_SERIAL_STAGES (bench.py's per-kernel timing pass): every kernel of a wave on one stream."""
+    from ngs_b200 import ffi
+    bam, bai, _ = _synth(1, 60000, level=1)
+    want = oracle_ints(bam, bai, gc_seed=4)
+    base = ffi.NGSQ_F_RECORD_FACETS | ffi.NGSQ_F_COVERAGE | ffi.NGSQ_F_VERIFY_CRC
+    for flags in (base, base | ffi.NGSQ_F_SERIAL_STAGES):
+        eng = ffi.Engine(flags=flags, gc_seed=4, launch_blocks=16)
+        got = engine_ints(bam, engine=eng, chunk_bytes=1 << 20)
+        assert got["stats"]["waves"] >= 5
+        assert_same_ints(got, want)
