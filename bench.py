@@ -177,7 +177,10 @@ def cpu_sample(args, wl):
     if shape == 3:
         # spliced reads: the reference's Coverage.process is O(span) and 60 % of these records span a ~100 kb intron
         # (coverage.rs:165-178 walks every skipped position): 3 M records would be minutes of one core
-        args = argparse.Namespace(**{**vars(args), "cpu_sample": min(args.cpu_sample, 400_000)})
+        # (measured: 101 s for the smallest chromosome of the 200 M-record BAM).  Whole contigs of a logical BAM at a quarter
+        # of the depth instead: the smallest chromosome then holds ~750 k records
+        args = argparse.Namespace(**{**vars(args), "cpu_sample": min(args.cpu_sample, 800_000)})
+        total = max(total // 4, 1_000_000)
     if shape == 2:
         n = max(2000, min(total, args.cpu_sample * 300 // 56000))
         bam, bai, info = ffi.synth_bam(shape, n, level=level)

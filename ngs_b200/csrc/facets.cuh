@@ -506,15 +506,15 @@ __global__ void __launch_bounds__(kFacetThreads) facets_kernel(FacetParams P) {
 }
 
 // ---- quality positions beyond the shared-memory tables (long reads) ----
-// Work item = (tile of kTilePos positions) x (chunk of the wave's LongRead list).  Inside a CTA every position of the tile
-// belongs to ONE lane (warp w, lane l: position 32 w + l), all warps walk the item's reads, and a lane counts its position's
-// score into its own row of 32-bit shared-memory counters with a plain load / add / store (shared-memory atomics run at
-// about one lane per clock per SM: profiles/round1_sanitizers.md).  The non-zero counters are then added to the global
-// table: one global reduction per (item, position, score) instead of one per base.
+// Work item = (tile of kTilePos positions) x (chunk of the wave's LongRead list).  A CTA tallies an item into 32-bit
+// shared-memory counters (lanes of one instruction hold distinct positions: no same-address conflicts), then adds the
+// non-zero counters to the global table: one global reduction per (item, position, score) instead of one per base.
+// (Measured alternative, rejected: one lane per position with plain load / add / store on a lane-owned row and all warps
+// walking every read of the item — no atomics, but eight times the serial iterations per warp: configs[3]'s facet stage
+// 511 ms against ~250 ms with this form.)
 constexpr uint32_t kTilePos = 256;
-constexpr uint32_t kTileThreads = kTilePos;        // one lane per position
+constexpr uint32_t kTileThreads = 256;
 constexpr uint32_t kTileSmem = kTilePos * 94 * 4;  // 94 KB: two CTAs per SM
-constexpr uint32_t kTileUnroll = 8;                // reads in flight per warp
 
 struct QualTileParams {
   const uint8_t* d;      // base of the wave's slot
@@ -537,41 +537,43 @@ __global__ void __launch_bounds__(kTileThreads) qual_tiles_kernel(QualTileParams
   const uint32_t max_chunks = (n_long + 63) / 64;
   if (n_chunks > max_chunks) n_chunks = max_chunks;
   const uint32_t per = (n_long + n_chunks - 1) / n_chunks;
-  const uint32_t lane = threadIdx.x & 31;
-  uint32_t* my_row = t_cnt + threadIdx.x * 94;  // this lane's position
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t i = threadIdx.x; i < kTilePos * 94; i += kTileThreads) t_cnt[i] = 0;
   __syncthreads();
   for (uint32_t item = blockIdx.x; item < n_tiles * n_chunks; item += gridDim.x) {
     const uint32_t tile = item / n_chunks, chunk = item - tile * n_chunks;
     const uint32_t p_lo = P.qpos_smem + tile * kTilePos;
-    const uint32_t p = p_lo + threadIdx.x;
     const uint32_t r0 = chunk * per, r1 = r0 + per < n_long ? r0 + per : n_long;
-    for (uint32_t r = r0; r < r1; r += kTileUnroll) {
-      uint32_t q[kTileUnroll], h[kTileUnroll], have[kTileUnroll];
+    for (uint32_t r = r0 + warp; r < r1; r += kTileThreads / 32) {
+      const uint32_t ls = P.list[r].ls;
+      if (ls <= p_lo) continue;  // warp-uniform
+      const uint8_t* ql = P.d + P.list[r].qoff;
+      uint32_t p_hi = ls < p_lo + kTilePos ? ls : p_lo + kTilePos;
+      if (p_hi > P.qpos_cap) p_hi = P.qpos_cap;
+      uint32_t q[kTilePos / 32];
 #pragma unroll
-      for (uint32_t j = 0; j < kTileUnroll; ++j) {
-        q[j] = h[j] = 0x100u;  // 0x100: no byte here
-        have[j] = 3u;
-        if (r + j < r1) {
-          const uint4 e = *reinterpret_cast<const uint4*>(&P.list[r + j]);  // {qoff lo, qoff hi, ls, flags}: the same address in every lane
-          const uint32_t ls = e.z;
-          if (ls > p_lo) {  // warp-uniform
-            const uint8_t* ql = P.d + ((uint64_t)e.y << 32 | e.x);
-            have[j] = e.w;
-            if (p < ls && p < P.qpos_cap) q[j] = __ldg(ql + p);
-            // the positions the facet kernel tallied: only their share of the verdict
-            if (tile == 0 && threadIdx.x < P.qpos_smem) h[j] = __ldg(ql + threadIdx.x);
-          }
-        }
+      for (uint32_t k = 0; k < kTilePos / 32; ++k) {
+        const uint32_t p = p_lo + lane + 32 * k;
+        q[k] = p < p_hi ? (uint32_t)__ldg(ql + p) : 0x100u;  // 0x100: beyond the string
       }
+      uint32_t q_min = 0x100u, q_max = 0;
 #pragma unroll
-      for (uint32_t j = 0; j < kTileUnroll; ++j) {
-        if (q[j] <= 93) my_row[q[j]] += 1;
-        const uint32_t lo = min(q[j], h[j]), hi = max(q[j] & 0xFFu, h[j] & 0xFFu);
-        uint32_t f = (lo < 0xFFu ? 1u : 0u) | (hi > 93 ? 2u : 0u);
-        f = __reduce_or_sync(0xFFFFFFFFu, f);
-        // other warps and other tiles of the same read set the same bits
-        if ((f & ~have[j]) && lane == 0) atomicOr(&P.list[r + j].flags, f);
+      for (uint32_t k = 0; k < kTilePos / 32; ++k) {
+        q_min = min(q_min, q[k]);
+        q_max = max(q_max, q[k] & 0xFFu);
+        if (q[k] <= 93) atomicAdd(&t_cnt[(lane + 32 * k) * 94 + q[k]], 1u);
+      }
+      if (tile == 0)  // the positions the facet kernel tallied: only their share of the verdict
+        for (uint32_t p = lane; p < P.qpos_smem; p += 32) {
+          const uint32_t v = __ldg(ql + p);
+          q_min = min(q_min, v);
+          q_max = max(q_max, v);
+        }
+      uint32_t f = (q_min < 0xFFu ? 1u : 0u) | (q_max > 93 ? 2u : 0u);
+      f = __reduce_or_sync(0xFFFFFFFFu, f);
+      if (f && lane == 0) {
+        const uint32_t have = *(volatile uint32_t*)&P.list[r].flags;  // other tiles of the same read set the same bits
+        if ((have | f) != have) atomicOr(&P.list[r].flags, f);
       }
     }
     __syncthreads();
