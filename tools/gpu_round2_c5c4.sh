@@ -3,7 +3,7 @@
 # checked against the full-size goldens.
 set -u
 mkdir -p gpurun_out
-for shape in c5 c4; do
+for shape in ${@:-c5 c4}; do
   (timeout 1300 python bench.py --shape $shape --steps 2 --warmup 3) > gpurun_out/r2_bench_$shape.json 2> gpurun_out/r2_bench_$shape.err; echo "$shape rc=$?"
   grep -E "generated|resident steps|serial-stages|Error|error" gpurun_out/r2_bench_$shape.err | tail -5
   python - $shape <<'PY'

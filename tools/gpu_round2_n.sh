@@ -17,5 +17,5 @@ except Exception as e:
     print("no bench line", e)
 PY
 if [ "$N" = "2" ]; then
-  (timeout 600 python -m pytest tests/test_gpu_host_driver.py -m gpu -q --timeout 300 -p no:cacheprovider) > gpurun_out/r2n_driver_tests.log 2>&1; tail -3 gpurun_out/r2n_driver_tests.log
+  (timeout 200 python -m pytest tests/test_gpu_host_driver.py -m gpu -q --timeout 180 -p no:cacheprovider -k "two_devices or devices") > gpurun_out/r2n_driver_tests.log 2>&1; tail -3 gpurun_out/r2n_driver_tests.log
 fi
