@@ -91,6 +91,8 @@ pub mod sys {
     pub const NGSQ_F_VERIFY_CRC: u32 = 4;
     pub const NGSQ_F_EDITS: u32 = 8;
     pub const NGSQ_F_FEATURES: u32 = 16;
+    /// measurement aid: every kernel of a wave on one stream (no overlap with the next wave's inflate); results identical
+    pub const NGSQ_F_SERIAL_STAGES: u32 = 32;
     pub const NGSQ_E_QUAL_CAP: c_int = -13;
 
     extern "C" {
