@@ -232,7 +232,9 @@ class Engine:
 
     def inflate_to_host(self, data: np.ndarray) -> np.ndarray:
         n = C.c_size_t(0)
-        cap = max(65536, int(data.size) * 64 + 65536)
+        # a BGZF block inflates to at most 64 KiB whatever its compressed size (a pile-up of identical records compresses 1000:1)
+        _, n_blocks, _ = bgzf_walk(data)
+        cap = (int(n_blocks) + 1) * 65536
         out = np.empty(cap, dtype=np.uint8)
         self._check(self.lib.ngsq_inflate_to_host(self.h, data.ctypes.data, data.size, out.ctypes.data, cap, C.byref(n)))
         return out[: n.value].copy()

@@ -252,3 +252,37 @@ def test_a_single_real_byte_makes_a_long_quality_string_present_and_its_0xff_byt
     bam, bai = write_bam(REFS, r)
     got = _check(bam, bai)
     assert got["quality"].shape[0] == 100
+
+
+def _pileup_bam(n, span=600):
+    """n identical records `1M{span-2}N1M` at one locus of a 5 kb contig (an amplicon seen through spliced two-base reads: the
+    depth without the bytes), BGZF blocks and BAI written directly — 8 M records through write_bam's per-record loop take minutes."""
+    refs = [("chr1", 5000)]
+    one = record(name="a", flag=0, ref=0, pos=1000, mapq=60, cigar=f"1M{span - 2}N1M", seq="AC", qual=[30, 30])
+    stream = np.tile(np.frombuffer(one, dtype=np.uint8), n).tobytes()
+    out = bytearray(bgzf_block(header_bytes(refs)))
+    first = len(out) << 16
+    for o in range(0, len(stream), 0xFF00):
+        out += bgzf_block(stream[o:o + 0xFF00], 1)
+    end = len(out) << 16
+    out += EOF_BLOCK
+    from bamutil import reg2bin
+    bai = bytearray(b"BAI\x01" + struct.pack("<i", 1))
+    bai += struct.pack("<i", 2)
+    bai += struct.pack("<Ii", reg2bin(1000, 1000 + span), 1) + struct.pack("<QQ", first, end)
+    bai += struct.pack("<IiQQQQ", 37450, 2, first, end, n, 0)
+    bai += struct.pack("<i", 1) + struct.pack("<Q", first)
+    bai += struct.pack("<Q", 0)
+    return bytes(out), bytes(bai)
+
+
+def test_pileup_deeper_than_2_23_keeps_the_carry_of_the_bin_sums():
+    """coverage.cuh reduces the per-lane bin sums of a warp's 512 positions as u64: two independent 32-bit halves would drop the
+    carry once they pass 2^32 — 8.4 M reads deep over the whole window (amplicon / rRNA depth)."""
+    n = 8_500_000
+    bam, bai = _pileup_bam(n)
+    b, i = as_u8(bam), as_u8(bai)
+    want = oracle_ints(b, i, gc_seed=3)
+    assert int(want["coverage"][0]["bin_sums"].sum()) == n * 600 > 1 << 32
+    got = engine_ints(b, gc_seed=3)
+    assert_same_ints(got, want)
