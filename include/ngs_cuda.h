@@ -213,6 +213,11 @@ int ngsq_get_coverage_global(ngsq_engine* e, uint64_t* nonsensical_records);
  * intergenic_count, exonic_count, intronic_count, processed, ignored_flags, ignored_nonprimary_chromosome. */
 int ngsq_get_features(ngsq_engine* e, uint64_t counts[9]);
 int ngsq_get_edits(ngsq_engine* e, uint64_t read_one[513], uint64_t read_two[513], uint64_t vaf[101], uint64_t* records);
+/* The VAF file of edits.rs:317-340 (`--vaf-file`): refs_per_position / alts_per_position of header sequence `ref` when its
+ * teardown runs, n = sequence length + 1 entries each, index = 1-based reference position (alignment_start + reference_ptr,
+ * edits.rs:279-281; entry 0 stays 0).  After ngsq_finish; with several engines every engine holds the counts of the records
+ * of its own shard (contig-exclusive shards: the owner's are the sequence's). */
+int ngsq_get_edit_positions(ngsq_engine* e, uint32_t ref, uint32_t* refs, uint32_t* alts, uint64_t n);
 int ngsq_get_stats(ngsq_engine* e, ngsq_stats* out);
 
 /* ---- multi-GPU merge: one sum-reduce of the packed u64 result buffer ---- */

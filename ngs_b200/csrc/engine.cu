@@ -1360,6 +1360,21 @@ int ngsq_get_edits(ngsq_engine* e, uint64_t read_one[513], uint64_t read_two[513
   return NGSQ_OK;
 }
 
+// Per-position counters of one header sequence for the VAF file (edits.rs:317-340): a plain read-back, positions are
+// 1-based like alignment_start + reference_ptr (edits.rs:279-281), entry 0 is never written.
+int ngsq_get_edit_positions(ngsq_engine* e, uint32_t ref, uint32_t* refs, uint32_t* alts, uint64_t n) {
+  if (!e) return NGSQ_E_ARG;
+  if (!e->finished || e->h_ed_res.size() != E_WORDS) return fail(e, NGSQ_E_ARG, "Edits results requested before ngsq_finish or without NGSQ_F_EDITS");
+  if (e->h_ed_res[E_ERR]) return fail(e, NGSQ_E_EDITS, "the Edits facet failed; no results");
+  if (ref >= e->n_ref || ref >= e->ed_contigs.size() || !refs || !alts) return fail(e, NGSQ_E_ARG, "ngsq_get_edit_positions: bad reference id or null output");
+  const EditsContig& c = e->ed_contigs[ref];
+  if (n != (uint64_t)c.hdr_len + 1) return fail(e, NGSQ_E_ARG, "ngsq_get_edit_positions: reference %u has %u + 1 positions, %llu requested", ref, c.hdr_len, (unsigned long long)n);
+  CU(cudaSetDevice(e->device));
+  CU(cudaMemcpy(refs, e->d_ed_refs + c.pos_off, n * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(alts, e->d_ed_alts + c.pos_off, n * 4, cudaMemcpyDeviceToHost));
+  return NGSQ_OK;
+}
+
 #define NEED_RESULTS()                                                                   \
   if (!e) return NGSQ_E_ARG;                                                             \
   if (!e->finished || e->h_res.empty()) return fail(e, NGSQ_E_ARG, "results requested before ngsq_finish")

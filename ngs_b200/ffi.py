@@ -36,7 +36,7 @@ EXPORTED = [
     "ngsq_get_tlen", "ngsq_get_gc", "ngsq_get_quality", "ngsq_get_coverage_contig", "ngsq_get_coverage_global",
     "ngsq_get_stats", "ngsq_nccl_unique_id", "ngsq_comm_init", "ngsq_reduce", "ngsq_set_quality_positions",
     "ngsq_result_buffer", "ngsq_refresh_results", "ngsq_host_alloc", "ngsq_host_free", "ngsq_inflate_to_host",
-    "ngsq_set_reference_bases", "ngsq_get_edits", "ngsq_set_feature_model", "ngsq_set_features", "ngsq_get_features",
+    "ngsq_set_reference_bases", "ngsq_get_edits", "ngsq_get_edit_positions", "ngsq_set_feature_model", "ngsq_set_features", "ngsq_get_features",
     "ngsq_wait_copied", "ngsq_host_register", "ngsq_host_unregister", "ngsq_flush", "ngsq_progress",
 ]
 
@@ -123,6 +123,7 @@ def load_library() -> C.CDLL:
     lib.ngsq_inflate_to_host.argtypes = [P, P, C.c_size_t, P, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.ngsq_set_reference_bases.argtypes = [P, C.c_uint32, P, C.c_uint64]
     lib.ngsq_get_edits.argtypes = [P, u64p, u64p, u64p, u64p]
+    lib.ngsq_get_edit_positions.argtypes = [P, C.c_uint32, u32p, u32p, C.c_uint64]
     lib.ngsq_set_feature_model.argtypes = [P, u8p, u8p]
     lib.ngsq_set_features.argtypes = [P, C.c_uint32, C.c_uint32, u32p, u32p, u8p]
     lib.ngsq_get_features.argtypes = [P, u64p]
@@ -291,6 +292,13 @@ class Engine:
         u64p = C.POINTER(C.c_uint64)
         self._check(self.lib.ngsq_get_edits(self.h, one.ctypes.data_as(u64p), two.ctypes.data_as(u64p), vaf.ctypes.data_as(u64p), C.byref(n)))
         return one, two, vaf, n.value
+
+    def edit_positions(self, ref: int, length: int):
+        """(refs[length + 1], alts[length + 1]) of header sequence `ref`, indexed by 1-based position (the VAF file's input)."""
+        refs, alts = np.zeros(length + 1, dtype=np.uint32), np.zeros(length + 1, dtype=np.uint32)
+        u32p = C.POINTER(C.c_uint32)
+        self._check(self.lib.ngsq_get_edit_positions(self.h, ref, refs.ctypes.data_as(u32p), alts.ctypes.data_as(u32p), length + 1))
+        return refs, alts
 
     # ---- Genomic Features (NGSQ_F_FEATURES) ----
     def set_feature_model(self, names, primary):

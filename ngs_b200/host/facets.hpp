@@ -6,6 +6,10 @@
 // facet pulls its exact integer state through the C ABI (`ingest`).  summarize()/teardown()/
 // aggregate() then run the reference's own float arithmetic on the host, in the same order.
 #pragma once
+#include <charconv>
+#include <fstream>
+#include <optional>
+#include <filesystem>
 #include <cmath>
 #include <memory>
 #include <stdexcept>
@@ -275,14 +279,22 @@ class GenomicFeaturesFacet : public RecordBasedQualityControlFacet {
   std::vector<std::string> primary_;
 };
 
-// ---- Edits (src/qc/sequence_based/edits.rs) — device path written, not yet verified on a GPU ----
+// ---- Edits (src/qc/sequence_based/edits.rs): process() and the VAF histogram of teardown() run on the device ----
 class EditsFacet : public SequenceBasedQualityControlFacet {
  public:
   EditMetrics metrics;
-  // edits.rs:64-105 (the VAF file option is not offered: per-position VAFs stay on the device)
-  static EditsFacet try_from(const std::string& reference_fasta) {
+  // edits.rs:117-161
+  static EditsFacet try_from(const std::string& reference_fasta, const std::optional<std::string>& vaf_file_path = std::nullopt) {
     EditsFacet f;
     f.sequences_ = read_fasta(slurp_maybe_gz(reference_fasta, "reference FASTA"));
+    if (vaf_file_path) {
+      if (std::filesystem::exists(*vaf_file_path))
+        throw std::runtime_error("refusing to overwrite existing VAF file: " + *vaf_file_path + ". Please delete and rerun if you'd like to replace it.");
+      f.vaf_file_ = std::make_unique<std::ofstream>(*vaf_file_path, std::ios::binary);
+      if (!*f.vaf_file_) throw std::runtime_error("creating VAF file");
+      *f.vaf_file_ << "Sequence\tPosition\tVAF\n";
+      if (!*f.vaf_file_) throw std::runtime_error("writing VAF file header");
+    }
     return f;
   }
   const char* name() const override { return "Edits"; }
@@ -295,6 +307,9 @@ class EditsFacet : public SequenceBasedQualityControlFacet {
       check(e, ngsq_set_reference_bases(e, (uint32_t)c, reinterpret_cast<const uint8_t*>(it->second.data()), it->second.size()));
     }
   }
+  // with several devices every engine holds the per-position counts of its own (contig-exclusive) shard
+  void set_engines(const std::vector<ngsq_engine*>& engines) { engines_ = engines; }
+  bool writes_vaf_file() const { return (bool)vaf_file_; }
   void ingest_global(ngsq_engine* e) override {
     std::vector<uint64_t> one(513), two(513), vaf(101);
     uint64_t records = 0;
@@ -303,15 +318,50 @@ class EditsFacet : public SequenceBasedQualityControlFacet {
     metrics.read_two_edits.fill_from(two.data(), 513);
     metrics.vaf_histogram.fill_from(vaf.data(), 101);
   }
-  void ingest(ngsq_engine*, uint32_t, const ReferenceSequence&) override {}
-  void teardown(const ReferenceSequence&) override {}  // edits.rs:305-334 ran on the device (edits_vaf_kernel)
+  // teardown of one sequence (edits.rs:305-340).  The VAF histogram came from the device (edits_vaf_kernel); the VAF file,
+  // when asked for, is written here from the sequence's per-position counters: one line per position a record's `M` covered.
+  void ingest(ngsq_engine* root, uint32_t ref, const ReferenceSequence& seq) override {
+    if (!vaf_file_) return;
+    const uint64_t n = (uint64_t)seq.length + 1;
+    std::vector<uint32_t> refs(n, 0), alts(n, 0), r(n), a(n);
+    std::vector<ngsq_engine*> engines = engines_.empty() ? std::vector<ngsq_engine*>{root} : engines_;
+    for (ngsq_engine* e : engines) {
+      check(e, ngsq_get_edit_positions(e, ref, r.data(), a.data(), n));
+      for (uint64_t i = 0; i < n; ++i) { refs[i] += r[i]; alts[i] += a[i]; }
+    }
+    std::string out;
+    char buf[64];
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint64_t total = (uint64_t)refs[i] + alts[i];
+      if (!total) continue;
+      out += seq.name;
+      out += '\t';
+      out += std::to_string(i);
+      out += '\t';
+      out.append(buf, format_f32_display(buf, sizeof buf, (float)alts[i] / (float)total));
+      out += '\n';
+      if (out.size() > (1u << 20)) { vaf_file_->write(out.data(), (std::streamsize)out.size()); out.clear(); }
+    }
+    vaf_file_->write(out.data(), (std::streamsize)out.size());
+    if (!*vaf_file_) throw std::runtime_error("writing VAF file");
+  }
+  void teardown(const ReferenceSequence&) override {}
   void aggregate(Results& results) override {          // edits.rs:336-344
     metrics.summary = std::make_pair(metrics.read_one_edits.mean(), metrics.read_two_edits.mean());
+    if (vaf_file_) vaf_file_->flush();
     results.edits = metrics;
+  }
+  // `{}` of an f32 in Rust: the shortest decimal that reads back as the same f32, positional, no exponent, no trailing ".0"
+  // (edits.rs:338).  std::to_chars in fixed notation without a precision is that representation.
+  static size_t format_f32_display(char* buf, size_t cap, float v) {
+    auto res = std::to_chars(buf, buf + cap, v, std::chars_format::fixed);
+    return (size_t)(res.ptr - buf);
   }
 
  private:
   std::map<std::string, std::string> sequences_;
+  std::unique_ptr<std::ofstream> vaf_file_;
+  std::vector<ngsq_engine*> engines_;
 };
 
 // src/qc.rs:44-126 — default facet set and the `--only` filter.  Genomic Features (needs a GFF)

@@ -205,7 +205,7 @@ int app(const QcArgs& args, const ReferenceGenome& genome, const std::string& ou
   std::unique_ptr<GenomicFeaturesFacet> features_facet;
   std::unique_ptr<EditsFacet> edits_facet;
   if (args.features_gff) features_facet = std::make_unique<GenomicFeaturesFacet>(GenomicFeaturesFacet::try_from(*args.features_gff, args.feature_names, genome));
-  if (args.reference_fasta) edits_facet = std::make_unique<EditsFacet>(EditsFacet::try_from(*args.reference_fasta));
+  if (args.reference_fasta) edits_facet = std::make_unique<EditsFacet>(EditsFacet::try_from(*args.reference_fasta, args.vaf_file_path));
   FacetSet facets = get_qc_facets(genome, args.only_facet, std::move(features_facet), std::move(edits_facet));
   GenomicFeaturesFacet* features = nullptr;
   EditsFacet* edits = nullptr;
@@ -303,6 +303,7 @@ int app(const QcArgs& args, const ReferenceGenome& genome, const std::string& ou
   // first pass: summarize (command.rs:328-330)
   for (auto& f : facets.record_based) { f->ingest(root); f->summarize(); }
   // second pass: per sequence in header order setup -> (process on the device) -> teardown (command.rs:356-396)
+  if (edits) edits->set_engines(engines);  // the VAF file reads every engine's per-position counters
   for (auto& f : facets.sequence_based) f->ingest_global(root);
   for (uint32_t c = 0; c < header.reference_sequences.size(); ++c) {
     const ReferenceSequence& seq = header.reference_sequences[c];
@@ -344,7 +345,6 @@ int qc(const QcArgs& args) {
   if (!genome)
     throw std::runtime_error("reference genome is not supported: " + args.reference_genome +
                              ". Did you set the correct reference genome?. Use the `list genomes` subcommand to see supported reference genomes.");
-  if (args.vaf_file_path) throw std::runtime_error("--vaf-file is not available on the CUDA engine (per-position VAFs stay on the device)");
   std::string prefix = args.output_prefix.value_or(std::filesystem::path(args.src).filename().string());
   std::string outdir = args.output_directory.value_or(std::filesystem::current_path().string());
   return app(args, *genome, prefix, outdir);

@@ -98,6 +98,24 @@ int ngsq_get_edits(ngsq_engine*, uint64_t read_one[513], uint64_t read_two[513],
   if (records) *records = g_next[9 + 1127];
   return 0;
 }
+// per-position counters from $NGSQ_FAKE_VAF: per reference id, in order, [u32 n][n x u32 refs][n x u32 alts]
+int ngsq_get_edit_positions(ngsq_engine*, uint32_t ref, uint32_t* refs, uint32_t* alts, uint64_t n) {
+  const char* p = getenv("NGSQ_FAKE_VAF");
+  FILE* f = p ? fopen(p, "rb") : nullptr;
+  if (!f) { fprintf(stderr, "fake engine: NGSQ_FAKE_VAF not readable\n"); exit(2); }
+  for (uint32_t c = 0;; ++c) {
+    uint32_t m = 0;
+    if (fread(&m, 4, 1, f) != 1) { fprintf(stderr, "fake engine: no counters for reference %u\n", ref); exit(2); }
+    std::vector<uint32_t> r(m), a(m);
+    if (m && (fread(r.data(), 4, m, f) != m || fread(a.data(), 4, m, f) != m)) { fprintf(stderr, "fake engine: short VAF file\n"); exit(2); }
+    if (c == ref) {
+      if (m != n) { fclose(f); return -1; }
+      memcpy(refs, r.data(), (size_t)m * 4); memcpy(alts, a.data(), (size_t)m * 4);
+      fclose(f);
+      return 0;
+    }
+  }
+}
 int ngsq_set_feature_model(ngsq_engine*, const uint8_t*, const uint8_t*) { return 0; }
 int ngsq_set_features(ngsq_engine*, uint32_t, uint32_t, const uint32_t*, const uint32_t*, const uint8_t*) { return 0; }
 int ngsq_set_reference_bases(ngsq_engine*, uint32_t, const uint8_t*, uint64_t) { return 0; }

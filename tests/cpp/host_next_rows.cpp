@@ -3,6 +3,7 @@
 //   host_next_rows gff <file> <5 names>      prints "seq start stop class" per kept feature, or "error: <message>"
 //   host_next_rows fasta <file>              prints "name length first-16-letters" per record
 //   host_next_rows json                      ingests the integers of $NGSQ_FAKE_NEXT and prints the results JSON
+//   host_next_rows vaf <fasta> <out> <name:len>...   EditsFacet with a VAF file: per-sequence ingest of $NGSQ_FAKE_VAF (edits.rs:317-340)
 #include <iostream>
 
 #include "../../ngs_b200/host/facets.hpp"
@@ -41,6 +42,24 @@ int main(int argc, char** argv) {
       ff.aggregate(r);
       ef.aggregate(r);
       std::cout << r.to_json_pretty();
+      return 0;
+    }
+    if (mode == "vaf" && argc >= 5) {
+      ngsq_engine* root = reinterpret_cast<ngsq_engine*>(1);
+      EditsFacet ef = EditsFacet::try_from(argv[2], std::string(argv[3]));
+      for (int k = 4; k < argc; ++k) {
+        const std::string a = argv[k];
+        ReferenceSequence seq;
+        seq.name = a.substr(0, a.find(':'));
+        seq.length = (uint32_t)std::stoul(a.substr(a.find(':') + 1));
+        ef.setup(seq);
+        ef.ingest(root, (uint32_t)(k - 4), seq);
+        ef.teardown(seq);
+      }
+      Results r;
+      ef.ingest_global(root);
+      ef.aggregate(r);
+      std::cout << "ok\n";
       return 0;
     }
   } catch (const std::exception& ex) {

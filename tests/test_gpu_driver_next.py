@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from test_oracle_edits import make_edits_case, oracle_edits  # noqa: E402
+from test_oracle_edits import _python_edits, make_edits_case, oracle_edits  # noqa: E402
 from test_oracle_features import KEYS, features, gff_line  # noqa: E402
 
 EXE = os.path.join(ROOT, "ngs_b200", "ngs-cuda-qc")
@@ -46,3 +46,28 @@ def test_results_json_carries_the_optional_facets(tmp_path):
     assert got == [want[k] for k in KEYS]
     assert (f["summary"]["ignored_flags_pct"], f["summary"]["ignored_nonprimary_chromosome_pct"]) == want["pct"]
     assert doc["general"]["records"]["total"] > 0 and doc["coverage"] is not None   # the default facets ran beside them
+
+
+def test_vaf_file_equals_the_restated_teardown(tmp_path):
+    """`--vaf-file` (edits.rs:108-113, 317-340): every position an `M` of a counted record covered, in header order, with the f32
+    VAF printed like Rust's `{}`; the per-position counters come off the device (ngsq_get_edit_positions)."""
+    bam, bai, fa, refseqs, recs = make_edits_case(31)
+    (tmp_path / "x.bam").write_bytes(bam)
+    (tmp_path / "x.bam.bai").write_bytes(bai)
+    (tmp_path / "ref.fa").write_bytes(fa)
+    vaf_path = tmp_path / "x.vaf.tsv"
+    cmd = [EXE, "qc", str(tmp_path / "x.bam"), "GRCh38_no_alt_AnalysisSet", "-o", str(tmp_path), "-p", "out",
+           "--reference-fasta", str(tmp_path / "ref.fa"), "--vaf-file", str(vaf_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = []
+    one, two, vaf, n = _python_edits(refseqs, recs, vaf_lines=lines)
+    got = vaf_path.read_text().splitlines()
+    assert got[0] == "Sequence\tPosition\tVAF" and len(lines) > 1000
+    assert got[1:] == lines
+    doc = json.load(open(tmp_path / "out.results.json"))
+    assert doc["edits"]["vaf_histogram"]["values"] == [int(x) for x in vaf]
+    assert sum(doc["edits"]["vaf_histogram"]["values"]) == len(lines)   # one histogram entry per line
+    # the reference refuses to overwrite (edits.rs:137-143)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode != 0 and "refusing to overwrite existing VAF file" in r.stderr

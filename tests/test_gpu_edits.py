@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 from bamutil import as_u8, rec, write_bam  # noqa: E402
 from test_edits_model import ERRORS, _one_record_case  # noqa: E402
-from test_oracle_edits import REFS, make_edits_case, oracle_edits  # noqa: E402
+from test_oracle_edits import REFS, _python_edits, make_edits_case, oracle_edits  # noqa: E402
 
 
 def _fasta_sequences(fa: bytes):
@@ -28,7 +28,7 @@ def _fasta_sequences(fa: bytes):
     return {k: "".join(v).encode() for k, v in out.items()}
 
 
-def engine_edits(bam: bytes, fa: bytes, record_facets=True, launch_blocks=0):
+def engine_edits(bam: bytes, fa: bytes, record_facets=True, launch_blocks=0, want_engine=False):
     """record_facets=False is `--only`-style: the one-record cases below carry a mapped pair without mate reference ids,
     on which the General facet of the reference panics (general.rs:81-83) before Edits ever sees the record."""
     from ngs_b200 import ffi, formats
@@ -44,6 +44,8 @@ def engine_edits(bam: bytes, fa: bytes, record_facets=True, launch_blocks=0):
     eng.set_range(hdr.first_voffset, 0)
     eng.submit(np.ascontiguousarray(b), 0)
     eng.finish()
+    if want_engine:
+        return eng, hdr
     return eng.edits(), eng.stats()
 
 
@@ -91,3 +93,20 @@ def test_a_contig_without_a_sequence_fails_only_if_it_holds_records():
     assert n == 1 and one[0] == 1 and int(vaf.sum()) == 20
     with pytest.raises(ffi.NgsqError):
         engine_edits(bam, b">chr2\nACGT\n", record_facets=False)
+
+
+def test_per_position_counters_match_the_restated_step_through():
+    """ngsq_get_edit_positions (the VAF file's input, edits.rs:279-288 / 317-340): refs and alts of every 1-based position."""
+    from ngs_b200 import ffi
+    bam, bai, fa, refseqs, recs = make_edits_case(5)
+    want = {}
+    _python_edits(refseqs, recs, positions=want)
+    for launch_blocks in (0, 2):
+        eng, hdr = engine_edits(bam, fa, launch_blocks=launch_blocks, want_engine=True)
+        for c, (name, L) in enumerate(hdr.refs):
+            refs, alts = eng.edit_positions(c, L)
+            np.testing.assert_array_equal(refs, want[c][0].astype(np.uint32), err_msg=f"refs of {name}")
+            np.testing.assert_array_equal(alts, want[c][1].astype(np.uint32), err_msg=f"alts of {name}")
+            assert refs[0] == 0 and alts[0] == 0
+        with pytest.raises(ffi.NgsqError):
+            eng.edit_positions(0, hdr.refs[0][1] + 1)   # the length must be the header's

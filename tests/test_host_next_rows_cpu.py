@@ -105,3 +105,37 @@ def test_features_and_edits_json_blocks(exe, tmp_path):
         return s / d
     assert e["summary"] == {"mean_edits_read_one": mean(one), "mean_edits_read_two": mean(two)}
     assert doc["general"] is None and doc["coverage"] is None
+
+
+def test_vaf_file_lines_follow_the_reference(exe, tmp_path):
+    """edits.rs:317-340: header line, then `name<TAB>1-based position<TAB>{f32}` for every position with refs + alts > 0, sequences in
+    header order; the f32 is printed like Rust's `{}` (shortest round-trip, positional, no trailing `.0`)."""
+    fa = tmp_path / "r.fa"
+    fa.write_text(">chr1\nACGT\n>chr2\nACGT\n")
+    n1, n2 = 11, 6
+    refs1, alts1 = np.zeros(n1, np.uint32), np.zeros(n1, np.uint32)
+    refs2, alts2 = np.zeros(n2, np.uint32), np.zeros(n2, np.uint32)
+    refs1[[1, 2, 3, 4, 5, 10]] = [1, 2, 1, 5, 999999, 0]
+    alts1[[1, 2, 3, 4, 5, 10]] = [0, 1, 1, 2, 1, 7]
+    refs2[[2, 5]] = [3, 70000]
+    alts2[[2, 5]] = [4, 30000]
+    with open(tmp_path / "pos.u32", "wb") as f:
+        for r, a in ((refs1, alts1), (refs2, alts2)):
+            f.write(np.array([r.size], np.uint32).tobytes() + r.tobytes() + a.tobytes())
+    one = np.zeros(9 + 513 + 513 + 101 + 1, np.uint64)
+    one.tofile(tmp_path / "next.u64")
+    out = tmp_path / "x.vaf.tsv"
+    env = {"NGSQ_FAKE_VAF": str(tmp_path / "pos.u32"), "NGSQ_FAKE_NEXT": str(tmp_path / "next.u64")}
+    assert run(exe, "vaf", str(fa), str(out), "chr1:10", "chr2:5", env=env) == "ok\n"
+    want = ["Sequence\tPosition\tVAF",
+            "chr1\t1\t0", "chr1\t2\t0.33333334", "chr1\t3\t0.5", "chr1\t4\t0.2857143", "chr1\t5\t0.000001", "chr1\t10\t1",
+            "chr2\t2\t0.5714286", "chr2\t5\t0.3"]
+    assert out.read_text().splitlines() == want
+    # the same strings from numpy's shortest round-trip formatting of the f32 quotient
+    for ln in want[1:]:
+        name, pos, v = ln.split("\t")
+        r, a = (refs1, alts1) if name == "chr1" else (refs2, alts2)
+        q = np.float32(a[int(pos)]) / np.float32(int(r[int(pos)]) + int(a[int(pos)]))
+        assert v == np.format_float_positional(q, unique=True, trim="-")
+    # an existing file is never overwritten (edits.rs:137-143)
+    assert "refusing to overwrite existing VAF file" in run(exe, "vaf", str(fa), str(out), "chr1:10", env=env)

@@ -74,7 +74,9 @@ def test_only_m_counts_as_a_comparison():
 REFS = [("chr1", 5000), ("chr2", 3000), ("chrM", 800)]
 
 
-def _python_edits(refseqs, recs):
+def _python_edits(refseqs, recs, positions=None, vaf_lines=None):
+    """positions (dict) / vaf_lines (list), when given, receive the per-position counters of every sequence and the lines of the
+    VAF file of edits.rs:317-340 (f32 printed like Rust's `{}`: shortest round-trip, positional)."""
     one, two, vaf = np.zeros(513, np.uint64), np.zeros(513, np.uint64), np.zeros(101, np.uint64)
     n = 0
     for c, (name, L) in enumerate(REFS):
@@ -98,9 +100,13 @@ def _python_edits(refseqs, recs):
             (one if r["flag"] & 0x40 else two)[e] += 1
             n += 1
         tot = refs + alts
+        if positions is not None:
+            positions[c] = (refs.copy(), alts.copy())
         for i in np.nonzero(tot)[0]:
             v = np.float32(alts[i]) / np.float32(tot[i])
             vaf[int(v * np.float32(100.0))] += 1
+            if vaf_lines is not None:
+                vaf_lines.append(f"{name}\t{i}\t" + np.format_float_positional(v, unique=True, trim="-"))
     return one, two, vaf, n
 
 
