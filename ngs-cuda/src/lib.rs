@@ -121,6 +121,7 @@ pub mod sys {
         pub fn ngsq_get_coverage_global(e: *mut NgsqEngine, nonsensical_records: *mut u64) -> c_int;
         pub fn ngsq_get_features(e: *mut NgsqEngine, counts: *mut u64) -> c_int;
         pub fn ngsq_get_edits(e: *mut NgsqEngine, read_one: *mut u64, read_two: *mut u64, vaf: *mut u64, records: *mut u64) -> c_int;
+        pub fn ngsq_get_edit_positions(e: *mut NgsqEngine, r: u32, refs: *mut u32, alts: *mut u32, n: u64) -> c_int;
         pub fn ngsq_get_stats(e: *mut NgsqEngine, out: *mut NgsqStats) -> c_int;
         pub fn ngsq_nccl_unique_id(out: *mut c_char) -> c_int;
         pub fn ngsq_comm_init(e: *mut NgsqEngine, n_ranks: c_int, rank: c_int, id: *const c_char) -> c_int;
@@ -337,6 +338,29 @@ impl Engine {
         let mut v = 0u64;
         self.check(unsafe { sys::ngsq_get_coverage_global(self.raw, &mut v) })?;
         Ok(v)
+    }
+
+    // ---- Edits / Genomic Features (Facets { edits, features }; inputs through the sys:: setters) ----
+    /// (read_one_edits `0..=512`, read_two_edits `0..=512`, vaf_histogram `0..=100`, records stepped through) of `EditMetrics`
+    /// when `aggregate()` runs (`edits.rs:22-46`, `:336-344`).
+    pub fn edits(&self) -> anyhow::Result<(Vec<u64>, Vec<u64>, Vec<u64>, u64)> {
+        let (mut one, mut two, mut vaf, mut n) = (vec![0u64; 513], vec![0u64; 513], vec![0u64; 101], 0u64);
+        self.check(unsafe { sys::ngsq_get_edits(self.raw, one.as_mut_ptr(), two.as_mut_ptr(), vaf.as_mut_ptr(), &mut n) })?;
+        Ok((one, two, vaf, n))
+    }
+    /// `refs_per_position` / `alts_per_position` of one header sequence at its teardown, indexed by 1-based position: what
+    /// `EditsFacet::teardown` iterates to write the VAF file (`edits.rs:317-340`).
+    pub fn edit_positions(&self, reference: u32, length: u32) -> anyhow::Result<(Vec<u32>, Vec<u32>)> {
+        let n = length as usize + 1;
+        let (mut refs, mut alts) = (vec![0u32; n], vec![0u32; n]);
+        self.check(unsafe { sys::ngsq_get_edit_positions(self.raw, reference, refs.as_mut_ptr(), alts.as_mut_ptr(), n as u64) })?;
+        Ok((refs, alts))
+    }
+    /// The nine counters of `GenomicFeaturesMetrics` in declaration order (`features/metrics.rs`).
+    pub fn features(&self) -> anyhow::Result<[u64; 9]> {
+        let mut c = [0u64; 9];
+        self.check(unsafe { sys::ngsq_get_features(self.raw, c.as_mut_ptr()) })?;
+        Ok(c)
     }
 
     // ---- multi-GPU: one Engine per device and thread, shards cut at the BAI's per-reference extents ----
