@@ -196,6 +196,7 @@ struct EditsParams {
   uint32_t* refs;
   uint32_t* alts;
   unsigned long long* res;     // E_* words
+  const uint32_t* mark;        // `-n`: 1 = the second pass processes this record (cov_n.cuh); nullptr = every record
 };
 
 __global__ void __launch_bounds__(256) edits_kernel(EditsParams P) {
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(256) edits_kernel(EditsParams P) {
   uint32_t n_counted = 0, err = 0;
   const uint64_t n_rec = P.st->fatal ? 0 : P.st->wave_rec;
   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (uint64_t)gridDim.x * blockDim.x) {
+    if (P.mark && !P.mark[r]) continue;  // not yielded, or behind the second pass's record counter
     const uint8_t* rec = P.d + (P.rec[r] & kRecOffMask);
     const int32_t ref = (int32_t)ed_ld32(rec + 4);
     uint32_t* refs = P.refs;

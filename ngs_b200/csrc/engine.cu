@@ -494,7 +494,7 @@ int ensure_wave_buffers(ngsq_engine* e, int s, uint32_t n, uint64_t bytes) {
     if ((rc = fresh(e, e->d_long, need_long, "long-read list"))) return rc;
     e->long_cap = need_long;
   }
-  if ((e->cfg.flags & NGSQ_F_COVERAGE) && e->cfg.max_records && need_rec > e->mark_cap) {
+  if ((e->cfg.flags & (NGSQ_F_COVERAGE | NGSQ_F_EDITS)) && e->cfg.max_records && need_rec > e->mark_cap) {
     if ((rc = quiesce())) return rc;
     if ((rc = fresh(e, e->d_mark, need_rec, "record marks"))) return rc;
     e->mark_cap = need_rec;
@@ -658,7 +658,9 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
       e->other_launches += 2;
     }
   }
-  if (cov_n) {
+  // `-n`: which records the second pass processes (one counter over all sequences) — Coverage and Edits share the marks
+  const bool pass2_n = (e->cfg.flags & (NGSQ_F_COVERAGE | NGSQ_F_EDITS)) && e->cfg.max_records;
+  if (pass2_n) {
     CovNParams C{};
     C.d = slot; C.rec = e->d_rec; C.st = e->d_state; C.max_records = e->cfg.max_records; C.n_ref = (int32_t)e->n_ref;
     C.ref_len = e->d_ref_len; C.cov_enabled = e->d_cov_enabled; C.diff_base = e->d_diff_base; C.diff = e->d_diff; C.cov_slot = e->d_cov_slot;
@@ -667,9 +669,9 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
     const uint32_t grid = (uint32_t)std::min<uint64_t>((bytes / 36 + 2 + 255) / 256, (uint64_t)e->n_sm * 8);
     cov_n_mark_kernel<<<grid, 256, 0, st>>>(C);
     cov_n_rank_kernel<<<1, 1024, 0, st>>>(C);
-    cov_n_apply_kernel<<<grid, 256, 0, st>>>(C);
+    if (cov_n) cov_n_apply_kernel<<<grid, 256, 0, st>>>(C);
     CU(cudaGetLastError());
-    e->other_launches += 3;
+    e->other_launches += cov_n ? 3 : 2;
   }
   const uint32_t rgrid = (uint32_t)std::min<uint64_t>((bytes / 36 + 2 + 255) / 256, (uint64_t)e->n_sm * 8);
   if ((e->cfg.flags & NGSQ_F_EDITS) && e->d_ed_res && e->ed_contigs.size() == e->n_ref) {
@@ -677,6 +679,7 @@ int launch_wave(ngsq_engine* e, uint32_t b0, uint32_t b1, bool final_wave) {
     EditsParams EP{};
     EP.d = slot; EP.rec = e->d_rec; EP.st = e->d_state; EP.n_ref = (int32_t)e->n_ref;
     EP.contigs = e->d_ed_contigs; EP.refs = e->d_ed_refs; EP.alts = e->d_ed_alts; EP.res = e->d_ed_res;
+    EP.mark = pass2_n ? e->d_mark : nullptr;
     edits_kernel<<<rgrid, 256, 0, st>>>(EP);
     CU(cudaGetLastError());
     e->other_launches++;

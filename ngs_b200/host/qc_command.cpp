@@ -217,7 +217,6 @@ int app(const QcArgs& args, const ReferenceGenome& genome, const std::string& ou
   if (coverage) flags |= NGSQ_F_COVERAGE;
   if (features) flags |= NGSQ_F_FEATURES;
   if (edits) flags |= NGSQ_F_EDITS;
-  if (args.num_records && edits) throw std::runtime_error("-n with --reference-fasta is not available on the CUDA engine (the second pass shares its record counter, command.rs:384-388)");
   if (args.verify_crc) flags |= NGSQ_F_VERIFY_CRC;
   if (args.num_records && n_dev > 1) throw std::runtime_error("-n needs a single device (records are counted in file order)");
 

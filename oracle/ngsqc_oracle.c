@@ -713,8 +713,12 @@ static int edits_find_contig(const char* fasta, size_t n, const char* name, uint
   return -1;
 }
 
-void* oracle_edits_run(const uint8_t* bam, size_t bam_len, const uint8_t* bai, size_t bai_len, const char* fasta, size_t fasta_len) {
+/* n_records: `-n` (0 = all).  Pass 2 keeps ONE counter over all sequences, incremented for every record a sequence's query yields —
+ * after the facets saw it, whether or not they skipped it — and reaching the limit only leaves the current sequence's loop
+ * (command.rs:375-388, display.rs:43-65). */
+void* oracle_edits_run_n(const uint8_t* bam, size_t bam_len, const uint8_t* bai, size_t bai_len, const char* fasta, size_t fasta_len, uint64_t n_records) {
   g_err[0] = 0;
+  uint64_t counter = 0;
   edits_t* E = calloc(1, sizeof *E);
   hist_init(&E->read_one, 512); hist_init(&E->read_two, 512); hist_init(&E->vaf, 100);
   bgzf_t* rd = malloc(sizeof *rd); recbuf_t rb = {malloc(1 << 16), 1 << 16}; rec_t rec;
@@ -728,7 +732,8 @@ void* oracle_edits_run(const uint8_t* bam, size_t bam_len, const uint8_t* bai, s
     if (edits_find_contig(fasta, fasta_len, refs[c].name, &seq, &seq_len)) { snprintf(g_err, sizeof g_err, "sequence %s not found in reference FASTA.", refs[c].name); return NULL; }
     uint64_t* refs_pp = calloc(L + 1, 8); uint64_t* alts_pp = calloc(L + 1, 8); /* zero_based_with_capacity(seq_length) */
     chunk_t* ch; size_t nch = bai_query(&B, c, 0, (int64_t)L, &ch);
-    for (size_t k = 0; k < nch; ++k) {
+    int stop = 0;
+    for (size_t k = 0; k < nch && !stop; ++k) {
       int src = bgzf_seek(rd, ch[k].beg); if (src < 0) return NULL; if (src == 0) break;
       while (bgzf_tell(rd) < ch[k].end) {
         int rc = read_record(rd, &rb, &rec, n_ref); if (rc < 0) return NULL; if (rc == 0) break;
@@ -736,7 +741,7 @@ void* oracle_edits_run(const uint8_t* bam, size_t bam_len, const uint8_t* bai, s
         uint64_t start = (uint64_t)rec.pos + 1, end = start + rec.span - 1;
         if (end == 0) continue;
         if (!(start <= L && end >= 1)) continue;
-        if (rec.flag & (0x4 | 0x400)) continue; /* unmapped or duplicate (edits.rs:227-229) */
+        if (!(rec.flag & (0x4 | 0x400))) { /* unmapped or duplicate: the facet returns at once (edits.rs:227-229) */
         { const char* nm = (const char*)rb.buf + 32; /* read name "*" = missing: the facet bails (edits.rs:233-236) */
           if (rec.l_name <= 1 || (rec.l_name == 2 && nm[0] == '*')) { snprintf(g_err, sizeof g_err, "Could not parse read name"); return NULL; } }
         /* reference slice start .. start + span, 1-based, end exclusive (edits.rs:241-243,259-262): out of the
@@ -759,6 +764,9 @@ void* oracle_edits_run(const uint8_t* bam, size_t bam_len, const uint8_t* bai, s
         /* increment(edits).unwrap(): more than 512 edits panics the reference (edits.rs:296-300) */
         if (hist_inc_by((rec.flag & 0x40) ? &E->read_one : &E->read_two, edits, 1)) { snprintf(g_err, sizeof g_err, "more than 512 edits in one read"); return NULL; }
         E->records++;
+        }
+        ++counter;
+        if (n_records && counter >= n_records) { stop = 1; break; }
       }
     }
     free(ch);
@@ -774,6 +782,9 @@ void* oracle_edits_run(const uint8_t* bam, size_t bam_len, const uint8_t* bai, s
   E->mean_read_two = hist_mean(&E->read_two);
   free(rd); free(rb.buf);
   return E;
+}
+void* oracle_edits_run(const uint8_t* bam, size_t bam_len, const uint8_t* bai, size_t bai_len, const char* fasta, size_t fasta_len) {
+  return oracle_edits_run_n(bam, bam_len, bai, bai_len, fasta, fasta_len, 0);
 }
 void oracle_edits_get(void* p, uint64_t read_one[513], uint64_t read_two[513], uint64_t vaf[101], double means[2], uint64_t* records) {
   edits_t* E = p;

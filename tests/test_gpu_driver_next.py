@@ -71,3 +71,20 @@ def test_vaf_file_equals_the_restated_teardown(tmp_path):
     # the reference refuses to overwrite (edits.rs:137-143)
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode != 0 and "refusing to overwrite existing VAF file" in r.stderr
+
+
+def test_num_records_with_reference_fasta(tmp_path):
+    """`-n` through the driver with Edits beside the default facets: pass 1 stops after n records, pass 2 follows its own counter."""
+    bam, bai, fa, _, _ = make_edits_case(11)
+    (tmp_path / "x.bam").write_bytes(bam)
+    (tmp_path / "x.bam.bai").write_bytes(bai)
+    (tmp_path / "ref.fa").write_bytes(fa)
+    r = subprocess.run([EXE, "qc", str(tmp_path / "x.bam"), "GRCh38_no_alt_AnalysisSet", "-o", str(tmp_path), "-p", "out", "-n", "161",
+                        "--reference-fasta", str(tmp_path / "ref.fa")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    doc = json.load(open(tmp_path / "out.results.json"))
+    one, two, vaf, n, means = oracle_edits(bam, bai, fa, n_records=161)
+    e = doc["edits"]
+    assert e["read_one_edits"]["values"] == [int(x) for x in one] and e["read_two_edits"]["values"] == [int(x) for x in two]
+    assert e["vaf_histogram"]["values"] == [int(x) for x in vaf]
+    assert doc["general"]["records"]["total"] == 161

@@ -28,13 +28,13 @@ def _fasta_sequences(fa: bytes):
     return {k: "".join(v).encode() for k, v in out.items()}
 
 
-def engine_edits(bam: bytes, fa: bytes, record_facets=True, launch_blocks=0, want_engine=False):
+def engine_edits(bam: bytes, fa: bytes, record_facets=True, launch_blocks=0, want_engine=False, n_records=0, coverage=True):
     """record_facets=False is `--only`-style: the one-record cases below carry a mapped pair without mate reference ids,
     on which the General facet of the reference panics (general.rs:81-83) before Edits ever sees the record."""
     from ngs_b200 import ffi, formats
     b = as_u8(bam)
-    eng = ffi.Engine(flags=(ffi.NGSQ_F_RECORD_FACETS if record_facets else 0) | ffi.NGSQ_F_COVERAGE | ffi.NGSQ_F_VERIFY_CRC | ffi.NGSQ_F_EDITS,
-                     launch_blocks=launch_blocks)
+    eng = ffi.Engine(flags=(ffi.NGSQ_F_RECORD_FACETS if record_facets else 0) | (ffi.NGSQ_F_COVERAGE if coverage else 0) | ffi.NGSQ_F_VERIFY_CRC
+                     | ffi.NGSQ_F_EDITS, launch_blocks=launch_blocks, max_records=n_records)
     hdr = formats.read_header(eng, b)
     eng.set_references([l for _, l in hdr.refs], [1 if formats.is_primary(n) else 0 for n, _ in hdr.refs])
     seqs = _fasta_sequences(fa)
@@ -110,3 +110,18 @@ def test_per_position_counters_match_the_restated_step_through():
             assert refs[0] == 0 and alts[0] == 0
         with pytest.raises(ffi.NgsqError):
             eng.edit_positions(0, hdr.refs[0][1] + 1)   # the length must be the header's
+
+
+@pytest.mark.parametrize("n", [1, 7, 161, 300])
+def test_num_records_follows_the_second_pass_counter(n):
+    """`-n` with Edits (command.rs:375-388): one counter over all sequences, incremented for every yielded record (also those
+    the facet skips), the limit only ends the current sequence's loop.  With and without Coverage beside it (they share the
+    marks of cov_n.cuh), one wave and many."""
+    bam, bai, fa, _, _ = make_edits_case(11)
+    one, two, vaf, cnt, _ = oracle_edits(bam, bai, fa, n_records=n)
+    for coverage, launch_blocks in ((True, 0), (False, 0), (True, 2)):
+        (g_one, g_two, g_vaf, g_n), _ = engine_edits(bam, fa, launch_blocks=launch_blocks, n_records=n, coverage=coverage)
+        assert g_n == cnt
+        np.testing.assert_array_equal(g_one, one)
+        np.testing.assert_array_equal(g_two, two)
+        np.testing.assert_array_equal(g_vaf, vaf)

@@ -20,6 +20,8 @@ def _lib():
     lib.oracle_stepthrough_edits.argtypes = [P, C.c_uint64, P, C.c_uint64, P, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.oracle_edits_run.restype = P
     lib.oracle_edits_run.argtypes = [P, C.c_size_t, P, C.c_size_t, C.c_char_p, C.c_size_t]
+    lib.oracle_edits_run_n.restype = P
+    lib.oracle_edits_run_n.argtypes = [P, C.c_size_t, P, C.c_size_t, C.c_char_p, C.c_size_t, C.c_uint64]
     lib.oracle_edits_get.argtypes = [P, P, P, P, P, C.POINTER(C.c_uint64)]
     return lib
 
@@ -74,15 +76,22 @@ def test_only_m_counts_as_a_comparison():
 REFS = [("chr1", 5000), ("chr2", 3000), ("chrM", 800)]
 
 
-def _python_edits(refseqs, recs, positions=None, vaf_lines=None):
+def _python_edits(refseqs, recs, positions=None, vaf_lines=None, n_records=0):
     """positions (dict) / vaf_lines (list), when given, receive the per-position counters of every sequence and the lines of the
     VAF file of edits.rs:317-340 (f32 printed like Rust's `{}`: shortest round-trip, positional)."""
     one, two, vaf = np.zeros(513, np.uint64), np.zeros(513, np.uint64), np.zeros(101, np.uint64)
     n = 0
+    counter = 0  # `-n`: one counter over all sequences, incremented after every yielded record (command.rs:375-388)
     for c, (name, L) in enumerate(REFS):
         refs, alts = np.zeros(L + 1, np.uint64), np.zeros(L + 1, np.uint64)
+        stop = False
         for r in recs:
-            if r["ref"] != c or r["flag"] & (0x4 | 0x400):
+            if r["ref"] != c or stop:   # every record of make_edits_case lies inside its sequence: the query yields it
+                continue
+            counter += 1
+            if n_records and counter >= n_records:
+                stop = True             # this record is still processed; the loop of THIS sequence ends after it
+            if r["flag"] & (0x4 | 0x400):
                 continue
             rp, qp, e = 0, 0, 0
             start = r["pos"] + 1
@@ -152,11 +161,11 @@ def make_edits_case(seed=17):
     return bam, bai, fasta.encode(), refseqs, recs
 
 
-def oracle_edits(bam: bytes, bai: bytes, fa: bytes):
+def oracle_edits(bam: bytes, bai: bytes, fa: bytes, n_records=0):
     """(read_one, read_two, vaf, records, means) from the oracle, or raises RuntimeError with its message."""
     lib = _lib()
     b, x = as_u8(bam), as_u8(bai)
-    h = lib.oracle_edits_run(b.ctypes.data, b.size, x.ctypes.data, x.size, fa, len(fa))
+    h = lib.oracle_edits_run_n(b.ctypes.data, b.size, x.ctypes.data, x.size, fa, len(fa), n_records)
     if not h:
         raise RuntimeError(lib.oracle_last_error().decode())
     one, two, vaf = np.zeros(513, np.uint64), np.zeros(513, np.uint64), np.zeros(101, np.uint64)
@@ -197,3 +206,18 @@ def test_lower_case_reference_bases_abort_the_run():
     b, x = as_u8(bam), as_u8(bai)
     assert not lib.oracle_edits_run(b.ctypes.data, b.size, x.ctypes.data, x.size, fasta, len(fasta))
     assert b"invalid base" in lib.oracle_last_error()
+
+
+@pytest.mark.parametrize("n", [1, 7, 150, 161, 300, 100000])
+def test_num_records_counts_every_yielded_record_and_only_ends_the_current_sequence(n):
+    """`-n` in pass 2 (command.rs:375-388): records the facet skips (unmapped / duplicate) count too, and once the limit is
+    reached every later sequence still contributes its first yielded record."""
+    bam, bai, fa, refseqs, recs = make_edits_case(11)
+    one, two, vaf, cnt = _python_edits(refseqs, recs, n_records=n)
+    o1, o2, ov, on, _ = oracle_edits(bam, bai, fa, n_records=n)
+    assert on == cnt
+    np.testing.assert_array_equal(o1, one)
+    np.testing.assert_array_equal(o2, two)
+    np.testing.assert_array_equal(ov, vaf)
+    if n == 1:
+        assert cnt <= len(REFS)   # at most one record per sequence
