@@ -340,7 +340,27 @@ impl Engine {
         Ok(v)
     }
 
-    // ---- Edits / Genomic Features (Facets { edits, features }; inputs through the sys:: setters) ----
+    // ---- Edits / Genomic Features (Facets { edits, features }) ----
+    /// `EditsFacet::setup` for header sequence `reference`: the letters of its FASTA record (`edits.rs:186-207`).  After
+    /// `set_references`, before the first chunk.
+    pub fn set_reference_bases(&mut self, reference: u32, letters: &[u8]) -> anyhow::Result<()> {
+        self.check(unsafe { sys::ngsq_set_reference_bases(self.raw, reference, letters.as_ptr(), letters.len() as u64) })
+    }
+    /// `slot_class[j]` = first of the five configured feature names (5' UTR, 3' UTR, CDS, exon, gene) equal to name j;
+    /// `primary[c]` = header sequence c belongs to the genome's primary assembly (`features.rs:131-140`, `:287-345`).
+    pub fn set_feature_model(&mut self, slot_class: &[u8], primary: &[u8]) -> anyhow::Result<()> {
+        if slot_class.len() != 5 {
+            bail!("ngs-cuda: five feature names expected");
+        }
+        self.check(unsafe { sys::ngsq_set_feature_model(self.raw, slot_class.as_ptr(), primary.as_ptr()) })
+    }
+    /// The kept GFF records of one header sequence: start, end as in the GFF, slot of their type.
+    pub fn set_features(&mut self, reference: u32, start: &[u32], stop: &[u32], class: &[u8]) -> anyhow::Result<()> {
+        if start.len() != stop.len() || start.len() != class.len() {
+            bail!("ngs-cuda: feature arrays differ in length");
+        }
+        self.check(unsafe { sys::ngsq_set_features(self.raw, reference, start.len() as u32, start.as_ptr(), stop.as_ptr(), class.as_ptr()) })
+    }
     /// (read_one_edits `0..=512`, read_two_edits `0..=512`, vaf_histogram `0..=100`, records stepped through) of `EditMetrics`
     /// when `aggregate()` runs (`edits.rs:22-46`, `:336-344`).
     pub fn edits(&self) -> anyhow::Result<(Vec<u64>, Vec<u64>, Vec<u64>, u64)> {
