@@ -231,7 +231,7 @@ class CoverageFacet : public SequenceBasedQualityControlFacet {
   uint64_t bin_size_;
 };
 
-// ---- Genomic Features (src/qc/record_based/features.rs) — device path written, not yet verified on a GPU ----
+// ---- Genomic Features (src/qc/record_based/features.rs): process() runs on the device (features.cuh) ----
 class GenomicFeaturesFacet : public RecordBasedQualityControlFacet {
  public:
   FeaturesMetrics metrics;
@@ -364,8 +364,8 @@ class EditsFacet : public SequenceBasedQualityControlFacet {
   std::vector<ngsq_engine*> engines_;
 };
 
-// src/qc.rs:44-126 — default facet set and the `--only` filter.  Genomic Features (needs a GFF)
-// and Edits (needs a reference FASTA) are not on the CUDA hot path.
+// src/qc.rs:44-126 — default facet set and the `--only` filter.  Genomic Features (needs a GFF) and Edits (needs a
+// reference FASTA) join it when their inputs were given, as in get_qc_facets.
 struct FacetSet {
   std::vector<std::unique_ptr<RecordBasedQualityControlFacet>> record_based;
   std::vector<std::unique_ptr<SequenceBasedQualityControlFacet>> sequence_based;

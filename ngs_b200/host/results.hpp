@@ -76,12 +76,12 @@ struct EditMetrics {
 // results.rs:24-45
 struct Results {
   std::optional<GeneralMetrics> general;
-  std::optional<FeaturesMetrics> features;  // filled only by the Genomic Features facet (device path not yet verified on a GPU)
+  std::optional<FeaturesMetrics> features;  // filled only by the Genomic Features facet
   std::optional<GCContentMetrics> gc_content;
   std::optional<TemplateLengthMetrics> template_length;
   std::optional<QualityScoreMetrics> quality_scores;
   std::optional<CoverageMetrics> coverage;
-  std::optional<EditMetrics> edits;         // filled only by the Edits facet (device path not yet verified on a GPU)
+  std::optional<EditMetrics> edits;         // filled only by the Edits facet
 
   static void write_hist(JsonWriter& w, const Histogram& h) {  // histogram.rs:152-159 field order
     w.begin_object();
