@@ -101,6 +101,9 @@ typedef struct ngsq_stats {
   uint64_t compressed_bytes; /* BGZF bytes submitted */
   uint64_t inflated_bytes;   /* sum of ISIZE */
   uint64_t max_read_len;     /* longest l_seq seen */
+  /* Stage times are sums over the waves of CUDA-event intervals on the stage's own stream.  The scan / facet / CRC kernels of
+   * wave k run beside the inflate of wave k+1, so the stages overlap (their sum exceeds ms_total) and each includes the time
+   * it shared the SMs with the others; NGSQ_F_SERIAL_STAGES gives the kernels' own times. */
   float ms_inflate;          /* device time of the inflate launches (bitmap clear + decode + resolve; CUDA events) */
   float ms_crc;
   float ms_scan;             /* record-boundary discovery + offset table */
